@@ -1,0 +1,195 @@
+"""ctypes loaders for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module.  Nothing under roargraph_b200/ imports it (tests/test_no_oracle_in_product.py enforces that).
+
+* ``Oracle``    -> oracle/liboracle.so        (plain-C restatement, oracle/roar_oracle.c)
+* ``Reference`` -> oracle/_ref/libref_roargraph.so (the reference's own code compiled unmodified, oracle/ref_capi.cpp)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+METRIC = {"l2": 0, "ip": 1, "cosine": 4}
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checkers (oracle/Makefile).  `ref` also builds oracle/_ref when /root/reference exists."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"] + (["ref"] if ref else []))
+
+
+def have_reference() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_roargraph.so"))
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.lib = L = C.CDLL(path)
+        L.orc_distance.restype = C.c_float
+        L.orc_distance.argtypes = [C.c_int, _f32p, _f32p, C.c_uint]
+        L.orc_normalize_rows.argtypes = [_f32p, C.c_uint64, C.c_uint]
+        L.orc_search_roargraph.restype = C.c_int
+        L.orc_search_roargraph.argtypes = [_f32p, C.c_uint64, C.c_uint, _u64p, _u32p, C.c_uint32, C.c_int, _f32p,
+                                           C.c_uint64, C.c_uint, C.c_uint, _u32p, _f32p, _u32p, _u32p, _u64p, _i32p,
+                                           C.c_int]
+        L.orc_search_bipartite.restype = C.c_int
+        L.orc_search_bipartite.argtypes = [_f32p, C.c_uint64, C.c_uint, _u64p, _u32p, _u32p, C.c_uint, C.c_int, _f32p,
+                                           C.c_uint64, C.c_uint, C.c_uint, _u32p, _f32p, _u32p, _u32p, _i32p, C.c_int]
+        L.orc_exact_knn.restype = C.c_int
+        L.orc_exact_knn.argtypes = [C.c_uint, C.c_uint, _i32p, _f32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_int,
+                                    C.c_int]
+        L.orc_num_procs.restype = C.c_int
+
+    def num_procs(self) -> int:
+        return int(self.lib.orc_num_procs())
+
+    def distance(self, metric: str, a, b) -> float:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        return float(self.lib.orc_distance(METRIC[metric], a, b, a.shape[0]))
+
+    def normalize_rows(self, x: np.ndarray) -> np.ndarray:
+        x = np.array(x, dtype=np.float32, order="C", copy=True)
+        self.lib.orc_normalize_rows(x, x.shape[0], x.shape[1])
+        return x
+
+    def search_roargraph(self, base, row_off, nbrs, ep, metric, queries, k, L, threads=0):
+        """base/queries: padded (x8) row-major float32, already normalised for cosine.
+        -> dict(ids, dists, cmps, hops, adj_words, status)"""
+        nq = queries.shape[0]
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        dists = np.zeros((nq, k), dtype=np.float32)
+        cmps = np.zeros(nq, dtype=np.uint32)
+        hops = np.zeros(nq, dtype=np.uint32)
+        adj = np.zeros(nq, dtype=np.uint64)
+        status = np.zeros(nq, dtype=np.int32)
+        nfail = self.lib.orc_search_roargraph(base, base.shape[0], base.shape[1], row_off, nbrs, int(ep),
+                                              METRIC[metric], queries, nq, k, L, ids, dists, cmps, hops, adj, status,
+                                              threads)
+        return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, adj_words=adj, status=status, nfail=nfail)
+
+    def search_bipartite(self, base, row_off, nbrs, init_ids, metric, queries, k, L, threads=0):
+        nq = queries.shape[0]
+        init_ids = np.ascontiguousarray(init_ids, dtype=np.uint32)
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        dists = np.zeros((nq, k), dtype=np.float32)
+        cmps = np.zeros(nq, dtype=np.uint32)
+        hops = np.zeros(nq, dtype=np.uint32)
+        status = np.zeros(nq, dtype=np.int32)
+        nfail = self.lib.orc_search_bipartite(base, base.shape[0], base.shape[1], row_off, nbrs, init_ids,
+                                              init_ids.shape[1], METRIC[metric], queries, nq, k, L, ids, dists, cmps,
+                                              hops, status, threads)
+        return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, status=status, nfail=nfail)
+
+    def exact_knn(self, base, queries, K, metric, threads=0):
+        """Unpadded row-major inputs, internal distances (IP negative), as exact_knn's contract."""
+        base = np.ascontiguousarray(base, dtype=np.float32)
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        ids = np.zeros((nq, K), dtype=np.int32)
+        dists = np.zeros((nq, K), dtype=np.float32)
+        rc = self.lib.orc_exact_knn(base.shape[1], K, ids, dists, base.shape[0], base, nq, queries, METRIC[metric],
+                                    threads)
+        if rc != 0:
+            raise RuntimeError("orc_exact_knn failed")
+        return ids, dists
+
+
+class Reference:
+    """The unmodified reference (prebuilt oracle/_ref/libref_roargraph.so; built from /root/reference when present)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_roargraph.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libref_roargraph.so missing: run `make -C oracle ref` where "
+                               "/root/reference is mounted")
+        self.lib = L = C.CDLL(path)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_num_procs.restype = C.c_int
+        L.ref_distance.restype = C.c_float
+        L.ref_distance.argtypes = [C.c_int, _f32p, _f32p, C.c_uint]
+        L.ref_build_roargraph.restype = C.c_int
+        L.ref_build_roargraph.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint,
+                                          C.c_uint, C.c_int]
+        L.ref_index_load.restype = C.c_void_p
+        L.ref_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_int]
+        L.ref_index_need_normalize.argtypes = [C.c_void_p]
+        L.ref_normalize_rows.argtypes = [_f32p, C.c_uint64, C.c_uint]
+        L.ref_search_roargraph.restype = C.c_int
+        L.ref_search_roargraph.argtypes = [C.c_void_p, _f32p, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_int, _u32p,
+                                           _f32p, _u32p, _u32p, C.POINTER(C.c_double)]
+        L.ref_index_free.argtypes = [C.c_void_p]
+        L.ref_index_base.restype = C.c_void_p
+        L.ref_index_base.argtypes = [C.c_void_p]
+
+    def err(self) -> str:
+        return self.lib.ref_last_error().decode()
+
+    def num_procs(self) -> int:
+        return int(self.lib.ref_num_procs())
+
+    def distance(self, metric: str, a, b) -> float:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        return float(self.lib.ref_distance(METRIC[metric], a, b, a.shape[0]))
+
+    def normalize_rows(self, x: np.ndarray) -> np.ndarray:
+        x = np.array(x, dtype=np.float32, order="C", copy=True)
+        self.lib.ref_normalize_rows(x, x.shape[0], x.shape[1])
+        return x
+
+    def build_roargraph(self, base_fbin, knn_file, out_index, metric, M_sq, M_pjbp, L_pjpq, threads, quiet=True):
+        rc = self.lib.ref_build_roargraph(base_fbin.encode(), knn_file.encode(), out_index.encode(), METRIC[metric],
+                                          M_sq, M_pjbp, L_pjpq, threads, int(quiet))
+        if rc != 0:
+            raise RuntimeError("reference build failed: " + self.err())
+
+    def index_load(self, base_fbin, index_file, metric, padded_dim, threads, quiet=True):
+        h = self.lib.ref_index_load(base_fbin.encode(), index_file.encode(), METRIC[metric], padded_dim, threads,
+                                    int(quiet))
+        if not h:
+            raise RuntimeError("reference index load failed: " + self.err())
+        return h
+
+    def index_base(self, h, nd, dim) -> np.ndarray:
+        """View of the reference's own (padded, maybe normalised) base array."""
+        ptr = self.lib.ref_index_base(h)
+        buf = (C.c_float * (nd * dim)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float32).reshape(nd, dim)
+
+    def search_roargraph(self, h, queries, k, L, threads, warmup=False):
+        nq = queries.shape[0]
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        dists = np.zeros((nq, k), dtype=np.float32)
+        cmps = np.zeros(nq, dtype=np.uint32)
+        hops = np.zeros(nq, dtype=np.uint32)
+        wall = C.c_double(0.0)
+        rc = self.lib.ref_search_roargraph(h, queries, nq, k, L, threads, int(warmup), ids, dists, cmps, hops,
+                                           C.byref(wall))
+        if rc != 0:
+            raise RuntimeError(self.err())
+        return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, wall_s=wall.value)
+
+    def index_free(self, h):
+        self.lib.ref_index_free(h)
+
+
+def run_ref_compute_groundtruth(base_fbin, query_fbin, gt_file, K, dist_fn, quiet=True):
+    """Run the reference's compute_groundtruth binary (compiled unmodified; MKL via torch's libtorch_cpu.so)."""
+    exe = os.path.join(HERE, "_ref", "ref_compute_groundtruth")
+    cmd = [exe, "--data_type", "float", "--dist_fn", dist_fn, "--base_file", base_fbin, "--query_file", query_fbin,
+           "--gt_file", gt_file, "--K", str(K)]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL if quiet else None)
