@@ -1,0 +1,126 @@
+/* rg_b200.h — C-ABI of the B200-native RoarGraph hot path (librg_b200.so).
+ *
+ * Drop-in boundary for the reference's distance-bound paths (paths relative to /root/reference):
+ *   - IndexBipartite::SearchRoarGraph        src/index_bipartite.cpp:2311-2420
+ *   - IndexBipartite::SearchBipartiteGraph   src/index_bipartite.cpp:282-356
+ *   - exact_knn (compute_groundtruth)        thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp:126-248
+ * The reference has no FFI of its own (single C++ process); these entry points are what its
+ * host code would bind at the `#pragma omp parallel for` over queries
+ * (tests/test_search_roargraph.cpp:203-209) and at the exact_knn call (compute_groundtruth.cpp:404).
+ * INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * RG_E* code, with a human-readable message in rg_last_error() (thread-local).  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with RG_ECUDA.
+ * An rg_index is not re-entrant: one host thread per index at a time (the reference shares one
+ * index among OpenMP threads; here the whole query batch crosses the boundary in one call).
+ */
+#ifndef RG_B200_H
+#define RG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* efanna2e::Metric values (include/efanna2e/distance.h:15).  COSINE is INNER_PRODUCT on rows the caller
+ * has already normalised, exactly as in the reference (src/index.cpp:16-20, src/index_bipartite.cpp:2679-2684,
+ * tests/test_search_roargraph.cpp:167-172). */
+#define RG_METRIC_L2 0
+#define RG_METRIC_INNER_PRODUCT 1
+#define RG_METRIC_COSINE 4
+
+#define RG_OK 0
+#define RG_EINVAL (-1)     /* bad argument */
+#define RG_ECUDA (-2)      /* CUDA runtime error / no device */
+#define RG_ENOTENOUGH (-3) /* "not enough results: N, expected: k"  (src/index_bipartite.cpp:2408-2412) */
+#define RG_ESTATE (-4)     /* graph not set, etc. */
+#define RG_ENOMEM (-5)
+
+typedef struct rg_index rg_index;
+
+const char *rg_last_error(void);
+/* ABI version of this header. */
+int rg_abi_version(void);
+/* Select the CUDA device this process drives (one process per GPU).  Optional; default device 0. */
+int rg_init(int device);
+/* Number of SMs etc. of the active device; returns <0 when no device is usable. */
+int rg_device_sm_count(void);
+
+/* ---- index lifetime ---------------------------------------------------------------------------
+ * base: nd x dim float32, row-major, row stride == dim, dim % 8 == 0 (the reference pads every row to x8
+ * floats with zeros, include/efanna2e/util.h:191-199 / :37-75, and constructs the index with the padded
+ * dim, tests/test_search_roargraph.cpp:132,160).  base_on_device != 0 means `base` is already a device
+ * pointer that outlives the index (no copy is made); otherwise it is a host pointer copied to HBM once.
+ * Replaces: IndexBipartite ctor + LoadSearchNeededData (include/index_bipartite.h:27,62). */
+int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim, int metric, int base_on_device);
+
+/* Projection graph as host CSR (row_off[nd+1], nbrs[row_off[nd]]) + entry point, i.e. the content of
+ * IndexBipartite::GetProjectionGraph() / LoadProjectionGraph (src/index_bipartite.cpp:2097-2117). */
+int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, const uint32_t *nbrs);
+
+/* Raw bipartite graph over n_total = nd + nd_sq nodes as host CSR (IndexBipartite::Load, :2058-2071). */
+int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_off, const uint32_t *nbrs);
+
+int rg_index_destroy(rg_index *idx);
+
+/* ---- SearchRoarGraph, whole batch -------------------------------------------------------------
+ * queries: nq x dim (same padded dim as the base; normalised by the caller for COSINE).
+ * Outputs (caller-allocated): ids[nq*k], dists[nq*k] = internal distances in (distance asc, id asc) order
+ * (-IP for ip/cosine, squared L2 for l2), cmps[nq] = distance evaluations excluding the entry point,
+ * hops[nq] = expansions — the pair SearchRoarGraph returns (:2354,2366,2397,2419).  cmps/hops may be NULL.
+ * Requires k <= L_pq (tests/test_search_roargraph.cpp:192-195).
+ * Host-buffer form: H2D of queries, kernel, D2H of results, synchronous. */
+int rg_search_roargraph(rg_index *idx, const float *queries, uint32_t nq, uint32_t k, uint32_t L_pq, uint32_t *ids,
+                        float *dists, uint32_t *cmps, uint32_t *hops);
+/* Device-buffer form: all pointers are device pointers, work is enqueued on `stream` (a cudaStream_t, may be
+ * NULL for the default stream) and the call returns without synchronising.  Query failures ("not enough
+ * results") are latched in the index and reported by rg_index_check(). */
+int rg_search_roargraph_dev(rg_index *idx, const float *d_queries, uint32_t nq, uint32_t k, uint32_t L_pq,
+                            uint32_t *d_ids, float *d_dists, uint32_t *d_cmps, uint32_t *d_hops, void *stream);
+/* Synchronise the index's work on `stream` and return RG_OK or the latched error of earlier *_dev calls. */
+int rg_index_check(rg_index *idx, void *stream);
+
+/* ---- SearchBipartiteGraph, whole batch ----------------------------------------------------------
+ * init_ids: nq x n_init base ids used as entry points (the reference draws 10 per query from an unseeded
+ * std::random_device, :287-294; pass them explicitly for reproducibility) or NULL to let the library draw
+ * n_init ids per query from `seed` (splitmix64 counter; uniform over [0, nd)). */
+int rg_search_bipartite(rg_index *idx, const float *queries, uint32_t nq, uint32_t k, uint32_t L_pq,
+                        const uint32_t *init_ids, uint32_t n_init, uint64_t seed, uint32_t *ids, float *dists,
+                        uint32_t *cmps, uint32_t *hops);
+int rg_search_bipartite_dev(rg_index *idx, const float *d_queries, uint32_t nq, uint32_t k, uint32_t L_pq,
+                            const uint32_t *d_init_ids, uint32_t n_init, uint64_t seed, uint32_t *d_ids,
+                            float *d_dists, uint32_t *d_cmps, uint32_t *d_hops, void *stream);
+
+/* ---- roofline accounting --------------------------------------------------------------------------
+ * Totals of the LAST search call on this index (synchronises): distance evaluations (unique, as the
+ * reference counts them), expansions, and the sum of out-degrees of the expanded nodes.  Algorithmic bytes
+ * per SURVEY.md 8(d) = (cmps + nq) * dim * 4 + adj_words * 4. */
+int rg_search_last_stats(rg_index *idx, uint64_t *total_cmps, uint64_t *total_hops, uint64_t *adj_words);
+/* Launch geometry chosen for the last search (for reporting): grid, block, dynamic smem bytes, rows per batch. */
+int rg_search_last_launch(rg_index *idx, uint32_t *grid, uint32_t *block, uint32_t *smem_bytes, uint32_t *rows_per_batch);
+
+/* ---- exact_knn ---------------------------------------------------------------------------------------
+ * Brute-force kNN of nq queries against nb base rows (row-major, row stride == dim, NO padding required,
+ * as compute_groundtruth reads raw fbin).  Outputs ids[nq*K] (int32, like the reference's closest_points) and
+ * dists[nq*K] = internal distances ascending: -IP for INNER_PRODUCT, squared L2 for L2, squared L2 of the
+ * normalised rows for COSINE (compute_groundtruth.cpp:146-174).  Candidate selection may run on tensor cores in
+ * bf16; every returned distance is recomputed in fp32.  id_offset is added to the ids (the reference's
+ * `start_id` for base parts, compute_groundtruth.cpp:413). */
+int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, uint32_t dim, uint32_t K, int metric,
+           int32_t id_offset, int32_t *ids, float *dists);
+int rg_knn_dev(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
+               int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, void *stream);
+
+/* Merge G per-shard top-K lists per query (each ascending) into one ascending top-K:
+ * the std::sort merge of compute_groundtruth.cpp:424-444 / the host merge of per-shard search results.
+ * in_dists/in_ids: [G][nq][K] device arrays (e.g. an ncclAllGather result); out: [nq][K]. */
+int rg_topk_merge_dev(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
+                      float *d_out_dists, uint32_t *d_out_ids, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RG_B200_H */

@@ -1,0 +1,242 @@
+"""roargraph_b200 — B200-native (sm_100a) implementation of RoarGraph's distance-bound hot path.
+
+This package is a thin ctypes binding over the C-ABI shared library ``librg_b200.so`` declared in
+``include/rg_b200.h`` (hand-written CUDA kernels, no CPU fallback).  It is what tests/ and bench.py call; the C++
+host mirror of the reference's ``efanna2e::IndexBipartite`` surface and the re-hosted CLIs live in ``host/``.
+
+Reference paths replaced (relative to /root/reference):
+  * IndexBipartite::SearchRoarGraph        src/index_bipartite.cpp:2311-2420
+  * IndexBipartite::SearchBipartiteGraph   src/index_bipartite.cpp:282-356
+  * exact_knn                              thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp:126-248
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librg_b200.so")
+
+METRIC_L2, METRIC_INNER_PRODUCT, METRIC_COSINE = 0, 1, 4  # efanna2e::Metric (include/efanna2e/distance.h:15)
+METRIC = {"l2": METRIC_L2, "ip": METRIC_INNER_PRODUCT, "cosine": METRIC_COSINE,
+          "mips": METRIC_INNER_PRODUCT}
+
+RG_OK, RG_EINVAL, RG_ECUDA, RG_ENOTENOUGH, RG_ESTATE, RG_ENOMEM = 0, -1, -2, -3, -4, -5
+
+
+class RgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+def build(verbose: bool = False) -> str:
+    """Compile librg_b200.so in-tree with nvcc for sm_100a (roargraph_b200/csrc/Makefile)."""
+    cmd = ["make", "-C", os.path.join(HERE, "csrc"), "-j", "4"]
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library.  Fails loudly when it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RgError(RG_ECUDA, f"{LIB_PATH} is missing: run roargraph_b200.build() / `make -C roargraph_b200/csrc` "
+                                    "(the product path has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+        L.rg_last_error.restype = C.c_char_p
+        L.rg_abi_version.restype = C.c_int
+        L.rg_init.argtypes = [C.c_int]
+        L.rg_device_sm_count.restype = C.c_int
+        L.rg_index_create.argtypes = [C.POINTER(vp), vp, u64, u32, C.c_int, C.c_int]
+        L.rg_index_set_graph.argtypes = [vp, u32, vp, vp]
+        L.rg_index_set_bipartite.argtypes = [vp, u64, vp, vp]
+        L.rg_index_destroy.argtypes = [vp]
+        L.rg_search_roargraph.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
+        L.rg_search_roargraph_dev.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp]
+        L.rg_index_check.argtypes = [vp, vp]
+        L.rg_search_bipartite.argtypes = [vp, vp, u32, u32, u32, vp, u32, u64, vp, vp, vp, vp]
+        L.rg_search_bipartite_dev.argtypes = [vp, vp, u32, u32, u32, vp, u32, u64, vp, vp, vp, vp, vp]
+        L.rg_search_last_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.rg_search_last_launch.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.rg_knn.argtypes = [vp, u64, vp, u64, u32, u32, C.c_int, i32, vp, vp]
+        L.rg_knn_dev.argtypes = [vp, u64, vp, u64, u32, u32, C.c_int, i32, vp, vp, vp]
+        L.rg_topk_merge_dev.argtypes = [vp, vp, u32, u64, u32, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RgError(rc, lib().rg_last_error().decode())
+
+
+def _np_ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def init(device: int = 0) -> None:
+    _check(lib().rg_init(device))
+
+
+def sm_count() -> int:
+    n = lib().rg_device_sm_count()
+    if n < 0:
+        _check(n)
+    return n
+
+
+def _stream_ptr(stream) -> C.c_void_p:
+    if stream is None:
+        return C.c_void_p(0)
+    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+
+class RoarIndex:
+    """Device-resident base vectors + graph(s); mirrors IndexBipartite's search-side surface for a whole batch.
+
+    ``base`` is either a C-contiguous float32 numpy array (copied to HBM once) or a CUDA torch tensor (used in
+    place; must outlive the index).  Row length must already be padded to a multiple of 8 (formats.pad_rows), and
+    rows must already be normalised for ``cosine`` — exactly what the reference's loader hands to its search
+    (src/index_bipartite.cpp:2664-2695).
+    """
+
+    def __init__(self, base, metric: str | int):
+        self._h = C.c_void_p(0)
+        m = METRIC[metric] if isinstance(metric, str) else int(metric)
+        self.metric = m
+        if isinstance(base, np.ndarray):
+            if base.dtype != np.float32 or not base.flags.c_contiguous or base.ndim != 2:
+                raise RgError(RG_EINVAL, "base must be a C-contiguous float32 matrix")
+            self._keep = None
+            self.nd, self.dim = base.shape
+            _check(lib().rg_index_create(C.byref(self._h), _np_ptr(base), self.nd, self.dim, m, 0))
+        else:  # torch CUDA tensor
+            if not base.is_cuda or not base.is_contiguous() or base.dim() != 2 or str(base.dtype) != "torch.float32":
+                raise RgError(RG_EINVAL, "base must be a contiguous float32 CUDA tensor")
+            self._keep = base
+            self.nd, self.dim = base.shape
+            _check(lib().rg_index_create(C.byref(self._h), C.c_void_p(base.data_ptr()), self.nd, self.dim, m, 1))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rg_index_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- graphs ------------------------------------------------------------------------------------------------
+    def set_graph(self, ep: int, row_off: np.ndarray, nbrs: np.ndarray) -> None:
+        """LoadProjectionGraph's content as CSR (src/index_bipartite.cpp:2097-2117)."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+        nbrs = np.ascontiguousarray(nbrs, dtype=np.uint32)
+        if row_off.shape[0] != self.nd + 1:
+            raise RgError(RG_EINVAL, "row_off must have nd + 1 entries")
+        _check(lib().rg_index_set_graph(self._h, int(ep), _np_ptr(row_off), _np_ptr(nbrs)))
+
+    def set_bipartite(self, row_off: np.ndarray, nbrs: np.ndarray) -> None:
+        """IndexBipartite::Load's content as CSR over nd + nd_sq nodes (src/index_bipartite.cpp:2058-2071)."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+        nbrs = np.ascontiguousarray(nbrs, dtype=np.uint32)
+        _check(lib().rg_index_set_bipartite(self._h, row_off.shape[0] - 1, _np_ptr(row_off), _np_ptr(nbrs)))
+
+    # -- SearchRoarGraph ---------------------------------------------------------------------------------------
+    def search(self, queries: np.ndarray, k: int, L_pq: int):
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call).
+        -> ids[nq,k] u32, dists[nq,k] f32 (internal distances), cmps[nq] u32, hops[nq] u32"""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise RgError(RG_EINVAL, "queries must be nq x dim (padded like the base)")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dists = np.empty((nq, k), dtype=np.float32)
+        cmps = np.empty(nq, dtype=np.uint32)
+        hops = np.empty(nq, dtype=np.uint32)
+        _check(lib().rg_search_roargraph(self._h, _np_ptr(q), nq, k, L_pq, _np_ptr(ids), _np_ptr(dists), _np_ptr(cmps),
+                                         _np_ptr(hops)))
+        return ids, dists, cmps, hops
+
+    def search_into(self, q: np.ndarray, k: int, L_pq: int, ids, dists, cmps, hops) -> None:
+        """Same call with caller-owned (e.g. pinned) host buffers; no allocation inside."""
+        _check(lib().rg_search_roargraph(self._h, _np_ptr(q), q.shape[0], k, L_pq, _np_ptr(ids), _np_ptr(dists),
+                                         _np_ptr(cmps) if cmps is not None else None,
+                                         _np_ptr(hops) if hops is not None else None))
+
+    def search_dev(self, d_q, k: int, L_pq: int, d_ids, d_dists, d_cmps=None, d_hops=None, stream=None) -> None:
+        """Device tensors (torch, int32/float32 storage), asynchronous on `stream`."""
+        _check(lib().rg_search_roargraph_dev(self._h, C.c_void_p(d_q.data_ptr()), d_q.shape[0], k, L_pq,
+                                             C.c_void_p(d_ids.data_ptr()), C.c_void_p(d_dists.data_ptr()),
+                                             C.c_void_p(d_cmps.data_ptr()) if d_cmps is not None else None,
+                                             C.c_void_p(d_hops.data_ptr()) if d_hops is not None else None,
+                                             _stream_ptr(stream)))
+
+    def check(self, stream=None) -> None:
+        _check(lib().rg_index_check(self._h, _stream_ptr(stream)))
+
+    # -- SearchBipartiteGraph ----------------------------------------------------------------------------------
+    def search_bipartite(self, queries: np.ndarray, k: int, L_pq: int, init_ids: np.ndarray | None = None,
+                         n_init: int = 10, seed: int = 0):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dists = np.empty((nq, k), dtype=np.float32)
+        cmps = np.empty(nq, dtype=np.uint32)
+        hops = np.empty(nq, dtype=np.uint32)
+        ip = None
+        if init_ids is not None:
+            init_ids = np.ascontiguousarray(init_ids, dtype=np.uint32)
+            n_init = init_ids.shape[1]
+            ip = _np_ptr(init_ids)
+        _check(lib().rg_search_bipartite(self._h, _np_ptr(q), nq, k, L_pq, ip, n_init, seed, _np_ptr(ids),
+                                         _np_ptr(dists), _np_ptr(cmps), _np_ptr(hops)))
+        return ids, dists, cmps, hops
+
+    # -- accounting --------------------------------------------------------------------------------------------
+    def last_stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().rg_search_last_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(cmps=a.value, hops=b.value, adj_words=c.value)
+
+    def last_launch(self):
+        g, b, s, r = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        _check(lib().rg_search_last_launch(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(r)))
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value, rows_per_batch=r.value)
+
+
+def knn(base: np.ndarray, queries: np.ndarray, K: int, metric: str | int, id_offset: int = 0):
+    """exact_knn's contract on host buffers: -> ids[nq,K] int32, dists[nq,K] float32 ascending internal distances."""
+    m = METRIC[metric] if isinstance(metric, str) else int(metric)
+    b = np.ascontiguousarray(base, dtype=np.float32)
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    ids = np.empty((q.shape[0], K), dtype=np.int32)
+    dists = np.empty((q.shape[0], K), dtype=np.float32)
+    _check(lib().rg_knn(_np_ptr(b), b.shape[0], _np_ptr(q), q.shape[0], b.shape[1], K, m, id_offset, _np_ptr(ids),
+                        _np_ptr(dists)))
+    return ids, dists
+
+
+def knn_dev(d_base, d_queries, K: int, metric: str | int, d_ids, d_dists, id_offset: int = 0, stream=None) -> None:
+    m = METRIC[metric] if isinstance(metric, str) else int(metric)
+    _check(lib().rg_knn_dev(C.c_void_p(d_base.data_ptr()), d_base.shape[0], C.c_void_p(d_queries.data_ptr()),
+                            d_queries.shape[0], d_base.shape[1], K, m, id_offset, C.c_void_p(d_ids.data_ptr()),
+                            C.c_void_p(d_dists.data_ptr()), _stream_ptr(stream)))
+
+
+def topk_merge_dev(d_in_dists, d_in_ids, d_out_dists, d_out_ids, stream=None) -> None:
+    """[G, nq, K] per-shard lists -> [nq, K] merged (compute_groundtruth.cpp:424-444)."""
+    G, nq, K = d_in_dists.shape
+    _check(lib().rg_topk_merge_dev(C.c_void_p(d_in_dists.data_ptr()), C.c_void_p(d_in_ids.data_ptr()), G, nq, K,
+                                   C.c_void_p(d_out_dists.data_ptr()), C.c_void_p(d_out_ids.data_ptr()),
+                                   _stream_ptr(stream)))

@@ -1,0 +1,467 @@
+// rg_capi.cu — the extern "C" boundary of librg_b200.so (include/rg_b200.h): index object, uploads, launches.
+// No CPU fallback anywhere: every compute entry point needs a CUDA device and fails with RG_ECUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rg_internal.h"
+
+namespace rg {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    cudaGetLastError();  // clear the sticky-less error state
+    return RG_ECUDA;
+}
+
+static int g_device = 0;
+static int g_sm_count = -1;
+
+static int ensure_device() {
+    if (g_sm_count > 0) return RG_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (librg_b200 has no CPU fallback)");
+        return RG_ECUDA;
+    }
+    RG_CUDA(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    RG_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    if (prop.major < 10) {
+        set_error("librg_b200 is built for sm_100a (B200) only");
+        return RG_ECUDA;
+    }
+    g_sm_count = prop.multiProcessorCount;
+    return RG_OK;
+}
+
+template <class T>
+struct DevBuf {  // grow-only device scratch
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return RG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        RG_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+        return RG_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace rg
+
+using namespace rg;
+
+struct rg_index {
+    uint64_t nd = 0;
+    uint32_t dim = 0;
+    int metric = 0;
+    const float *d_base = nullptr;
+    bool own_base = false;
+    // projection graph, fixed-stride rows [deg, ids...]
+    uint32_t *d_adj = nullptr;
+    uint32_t adj_stride = 0, ep = 0, max_deg = 0;
+    bool has_graph = false;
+    // bipartite graph, CSR
+    uint64_t *d_row_off = nullptr;
+    uint32_t *d_csr = nullptr;
+    uint64_t n_total = 0;
+    bool has_bipartite = false;
+    // visited tags
+    uint8_t *d_tags = nullptr;
+    uint32_t *d_slot_epoch = nullptr;
+    uint32_t n_slots = 0;
+    uint64_t tag_stride = 0;
+    // per-call scratch
+    uint32_t *d_counter = nullptr;
+    unsigned long long *d_stats = nullptr;
+    DevBuf<float> q, dists;
+    DevBuf<uint32_t> ids, cmps, hops, init;
+    SearchLaunch last_launch{};
+    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+};
+
+static int ensure_tags(rg_index *idx, uint32_t slots) {
+    if (slots <= idx->n_slots) return RG_OK;
+    if (idx->d_tags) cudaFree(idx->d_tags);
+    if (idx->d_slot_epoch) cudaFree(idx->d_slot_epoch);
+    idx->d_tags = nullptr;
+    idx->d_slot_epoch = nullptr;
+    idx->n_slots = 0;
+    const size_t bytes = (size_t)slots * idx->tag_stride;
+    RG_CUDA(cudaMalloc(&idx->d_tags, bytes));
+    RG_CUDA(cudaMalloc(&idx->d_slot_epoch, slots * sizeof(uint32_t)));
+    RG_CUDA(cudaMemset(idx->d_tags, 0, bytes));
+    RG_CUDA(cudaMemset(idx->d_slot_epoch, 0, slots * sizeof(uint32_t)));
+    idx->n_slots = slots;
+    return RG_OK;
+}
+
+// Number of query slots (resident warps) whose tag arrays fit in a bounded share of free HBM.
+static uint32_t affordable_slots(rg_index *idx) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 64;
+    size_t budget = (free_b + (size_t)idx->n_slots * idx->tag_stride) / 3;  // at most a third of what is free
+    size_t s = budget / idx->tag_stride;
+    if (s < 4) s = 4;
+    if (s > max_search_slots(g_sm_count)) s = max_search_slots(g_sm_count);
+    return (uint32_t)s;
+}
+
+static int fill_params(rg_index *idx, SearchParams &p, uint32_t nq, uint32_t k, uint32_t L) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    if (k == 0 || k > L) { set_error("L_pq must greater or equal than k"); return RG_EINVAL; }  // CLI :192-195
+    if (L >= (1u << 20)) { set_error("L_pq too large"); return RG_EINVAL; }
+    memset(&p, 0, sizeof(p));
+    p.base = idx->d_base;
+    p.nd = (uint32_t)idx->nd;
+    p.dim = idx->dim;
+    p.nq = nq;
+    p.k = k;
+    p.L = L;
+    p.metric_l2 = idx->metric == RG_METRIC_L2 ? 1 : 0;
+    p.tag_stride = idx->tag_stride;
+    p.counter = idx->d_counter;
+    p.stats = idx->d_stats;
+    return RG_OK;
+}
+
+static int check_latched(rg_index *idx) {
+    unsigned long long st[4];
+    RG_CUDA(cudaMemcpy(st, idx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[3] & 1ull) {
+        // same text as the reference's runtime_error (src/index_bipartite.cpp:2408-2412)
+        char buf[96];
+        snprintf(buf, sizeof(buf), "not enough results: %u, expected: k", (unsigned)(st[3] >> 32));
+        set_error(buf);
+        return RG_ENOTENOUGH;
+    }
+    return RG_OK;
+}
+
+extern "C" {
+
+const char *rg_last_error(void) { return g_err.c_str(); }
+int rg_abi_version(void) { return 1; }
+
+int rg_init(int device) {
+    g_device = device;
+    g_sm_count = -1;
+    return ensure_device();
+}
+
+int rg_device_sm_count(void) {
+    int rc = ensure_device();
+    return rc == RG_OK ? g_sm_count : rc;
+}
+
+int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim, int metric, int base_on_device) {
+    if (!out || !base || nd == 0 || dim == 0) { set_error("rg_index_create: null/empty argument"); return RG_EINVAL; }
+    if (dim % 8 != 0) { set_error("rg_index_create: dim must be padded to a multiple of 8 (util.h data_align)"); return RG_EINVAL; }
+    if (nd >= 0x7fffffffull) { set_error("rg_index_create: nd must be < 2^31"); return RG_EINVAL; }
+    if (metric != RG_METRIC_L2 && metric != RG_METRIC_INNER_PRODUCT && metric != RG_METRIC_COSINE) {
+        set_error("rg_index_create: unknown metric");
+        return RG_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    rg_index *idx = new rg_index();
+    idx->nd = nd;
+    idx->dim = dim;
+    idx->metric = metric;
+    idx->tag_stride = (nd + 15) & ~15ull;
+    if (base_on_device) {
+        idx->d_base = base;
+    } else {
+        float *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, nd * dim * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(d, base, nd * dim * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (d) cudaFree(d);
+            delete idx;
+            return cuda_fail(e, "base upload");
+        }
+        idx->d_base = d;
+        idx->own_base = true;
+    }
+    cudaError_t e = cudaMalloc(&idx->d_counter, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_stats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(idx->d_stats, 0, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        rg_index_destroy(idx);
+        return cuda_fail(e, "index scratch");
+    }
+    *out = idx;
+    return RG_OK;
+}
+
+int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, const uint32_t *nbrs) {
+    if (!idx || !row_off || (!nbrs && row_off[idx->nd] != 0)) { set_error("rg_index_set_graph: null argument"); return RG_EINVAL; }
+    if (ep >= idx->nd) { set_error("rg_index_set_graph: entry point out of range"); return RG_EINVAL; }
+    const uint64_t nd = idx->nd;
+    // Pass 1: duplicate-free degree of every row.  The reference's visited array makes a repeated id inside one
+    // adjacency list a no-op (src/index_bipartite.cpp:2378), so dropping repeats at upload changes nothing observable.
+    std::vector<uint32_t> tmp;
+    uint32_t max_deg = 0;
+    for (uint64_t u = 0; u < nd; ++u) {
+        if (row_off[u + 1] < row_off[u]) { set_error("rg_index_set_graph: row_off not monotone"); return RG_EINVAL; }
+        const uint64_t deg = row_off[u + 1] - row_off[u];
+        if (deg > max_deg) max_deg = (uint32_t)std::min<uint64_t>(deg, 0xffffffffu);
+    }
+    if (max_deg > 4096) { set_error("rg_index_set_graph: out-degree above 4096 is not supported by the fixed-stride layout"); return RG_EINVAL; }
+    const uint32_t stride = (max_deg + 1 + 7) & ~7u;  // [deg, ids...] padded to whole 32-byte sectors
+    std::vector<uint32_t> host((size_t)nd * stride, 0xffffffffu);
+    for (uint64_t u = 0; u < nd; ++u) {
+        uint32_t *row = host.data() + (size_t)u * stride;
+        uint32_t d = 0;
+        for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
+            const uint32_t v = nbrs[j];
+            if (v >= nd) { set_error("rg_index_set_graph: neighbour id out of range"); return RG_EINVAL; }
+            bool dup = false;
+            for (uint32_t i = 0; i < d; ++i)
+                if (row[1 + i] == v) { dup = true; break; }
+            if (!dup) row[1 + d++] = v;
+        }
+        row[0] = d;
+    }
+    if (idx->d_adj) cudaFree(idx->d_adj);
+    idx->d_adj = nullptr;
+    RG_CUDA(cudaMalloc(&idx->d_adj, host.size() * sizeof(uint32_t)));
+    RG_CUDA(cudaMemcpy(idx->d_adj, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    idx->adj_stride = stride;
+    idx->max_deg = max_deg;
+    idx->ep = ep;
+    idx->has_graph = true;
+    return RG_OK;
+}
+
+int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_off, const uint32_t *nbrs) {
+    if (!idx || !row_off || n_total < idx->nd) { set_error("rg_index_set_bipartite: bad argument"); return RG_EINVAL; }
+    // dedupe each list (same argument as in rg_index_set_graph) while rebuilding the CSR
+    std::vector<uint64_t> ro(n_total + 1, 0);
+    std::vector<uint32_t> out;
+    out.reserve(row_off[n_total]);
+    for (uint64_t u = 0; u < n_total; ++u) {
+        const size_t start = out.size();
+        for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
+            const uint32_t v = nbrs[j];
+            if (v >= n_total) { set_error("rg_index_set_bipartite: neighbour id out of range"); return RG_EINVAL; }
+            // query nodes (u >= nd) must point at base nodes: they are evaluated against the base array (:334)
+            if (u >= idx->nd && v >= idx->nd) { set_error("rg_index_set_bipartite: query node points at a query node"); return RG_EINVAL; }
+            if (std::find(out.begin() + start, out.end(), v) == out.end()) out.push_back(v);
+        }
+        ro[u + 1] = out.size();
+    }
+    if (idx->d_row_off) cudaFree(idx->d_row_off);
+    if (idx->d_csr) cudaFree(idx->d_csr);
+    idx->d_row_off = nullptr;
+    idx->d_csr = nullptr;
+    RG_CUDA(cudaMalloc(&idx->d_row_off, ro.size() * sizeof(uint64_t)));
+    RG_CUDA(cudaMalloc(&idx->d_csr, std::max<size_t>(out.size(), 1) * sizeof(uint32_t)));
+    RG_CUDA(cudaMemcpy(idx->d_row_off, ro.data(), ro.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (!out.empty()) RG_CUDA(cudaMemcpy(idx->d_csr, out.data(), out.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    idx->n_total = n_total;
+    idx->has_bipartite = true;
+    return RG_OK;
+}
+
+int rg_index_destroy(rg_index *idx) {
+    if (!idx) return RG_OK;
+    if (idx->own_base && idx->d_base) cudaFree((void *)idx->d_base);
+    if (idx->d_adj) cudaFree(idx->d_adj);
+    if (idx->d_row_off) cudaFree(idx->d_row_off);
+    if (idx->d_csr) cudaFree(idx->d_csr);
+    if (idx->d_tags) cudaFree(idx->d_tags);
+    if (idx->d_slot_epoch) cudaFree(idx->d_slot_epoch);
+    if (idx->d_counter) cudaFree(idx->d_counter);
+    if (idx->d_stats) cudaFree(idx->d_stats);
+    idx->q.release();
+    idx->dists.release();
+    idx->ids.release();
+    idx->cmps.release();
+    idx->hops.release();
+    idx->init.release();
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+    return RG_OK;
+}
+
+static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t nq, uint32_t k, uint32_t L,
+                      const uint32_t *d_init, uint32_t n_init, uint64_t seed, uint32_t *d_ids, float *d_dists,
+                      uint32_t *d_cmps, uint32_t *d_hops, cudaStream_t s) {
+    SearchParams p;
+    int rc = fill_params(idx, p, nq, k, L);
+    if (rc != RG_OK) return rc;
+    if (nq == 0) return RG_OK;
+    if (!d_q || !d_ids || !d_dists) { set_error("search: null buffer"); return RG_EINVAL; }
+    if (bipartite) {
+        if (!idx->has_bipartite) { set_error("search: bipartite graph not set"); return RG_ESTATE; }
+        if (n_init == 0 || n_init > (uint32_t)kCandCap) { set_error("search: n_init must be in [1, 96]"); return RG_EINVAL; }
+        p.row_off = idx->d_row_off;
+        p.csr_nbrs = idx->d_csr;
+        p.init_ids = d_init;
+        p.n_init = n_init;
+        p.seed = seed;
+    } else {
+        if (!idx->has_graph) { set_error("search: projection graph not set"); return RG_ESTATE; }
+        p.adj = idx->d_adj;
+        p.adj_stride = idx->adj_stride;
+        p.ep = idx->ep;
+        const char *pf = getenv("RG_PREFETCH_ADJ");
+        p.n_init = (pf && pf[0] == '0') ? 0u : 1u;  // doubles as the adjacency-prefetch switch
+    }
+    p.queries = d_q;
+    p.out_ids = d_ids;
+    p.out_dists = d_dists;
+    p.out_cmps = d_cmps;
+    p.out_hops = d_hops;
+    SearchLaunch l;
+    rc = plan_search(p, l, g_sm_count, std::max(idx->n_slots, affordable_slots(idx)));
+    if (rc != RG_OK) return rc;
+    rc = ensure_tags(idx, l.grid * l.warps_per_cta);
+    if (rc != RG_OK) return rc;
+    p.tags = idx->d_tags;
+    p.slot_epoch = idx->d_slot_epoch;
+    idx->last_launch = l;
+    return bipartite ? launch_bipartite(p, l, s) : launch_roargraph(p, l, s);
+}
+
+int rg_search_roargraph_dev(rg_index *idx, const float *d_queries, uint32_t nq, uint32_t k, uint32_t L_pq,
+                            uint32_t *d_ids, float *d_dists, uint32_t *d_cmps, uint32_t *d_hops, void *stream) {
+    return search_dev(idx, false, d_queries, nq, k, L_pq, nullptr, 0, 0, d_ids, d_dists, d_cmps, d_hops,
+                      (cudaStream_t)stream);
+}
+
+int rg_search_bipartite_dev(rg_index *idx, const float *d_queries, uint32_t nq, uint32_t k, uint32_t L_pq,
+                            const uint32_t *d_init_ids, uint32_t n_init, uint64_t seed, uint32_t *d_ids,
+                            float *d_dists, uint32_t *d_cmps, uint32_t *d_hops, void *stream) {
+    return search_dev(idx, true, d_queries, nq, k, L_pq, d_init_ids, n_init, seed, d_ids, d_dists, d_cmps, d_hops,
+                      (cudaStream_t)stream);
+}
+
+int rg_index_check(rg_index *idx, void *stream) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    RG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return check_latched(idx);
+}
+
+static int search_host(rg_index *idx, bool bipartite, const float *q, uint32_t nq, uint32_t k, uint32_t L,
+                       const uint32_t *init_ids, uint32_t n_init, uint64_t seed, uint32_t *ids, float *dists,
+                       uint32_t *cmps, uint32_t *hops) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    if (!q || !ids || !dists) { set_error("search: null buffer"); return RG_EINVAL; }
+    int rc;
+    if ((rc = idx->q.reserve((size_t)nq * idx->dim)) != RG_OK) return rc;
+    if ((rc = idx->ids.reserve((size_t)nq * k)) != RG_OK) return rc;
+    if ((rc = idx->dists.reserve((size_t)nq * k)) != RG_OK) return rc;
+    if ((rc = idx->cmps.reserve(nq)) != RG_OK) return rc;
+    if ((rc = idx->hops.reserve(nq)) != RG_OK) return rc;
+    cudaStream_t s = idx->stream;
+    RG_CUDA(cudaMemcpyAsync(idx->q.p, q, (size_t)nq * idx->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    const uint32_t *d_init = nullptr;
+    if (bipartite && init_ids) {
+        if ((rc = idx->init.reserve((size_t)nq * n_init)) != RG_OK) return rc;
+        RG_CUDA(cudaMemcpyAsync(idx->init.p, init_ids, (size_t)nq * n_init * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        d_init = idx->init.p;
+    }
+    rc = search_dev(idx, bipartite, idx->q.p, nq, k, L, d_init, n_init, seed, idx->ids.p, idx->dists.p, idx->cmps.p,
+                    idx->hops.p, s);
+    if (rc != RG_OK) return rc;
+    RG_CUDA(cudaMemcpyAsync(ids, idx->ids.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaMemcpyAsync(dists, idx->dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (cmps) RG_CUDA(cudaMemcpyAsync(cmps, idx->cmps.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (hops) RG_CUDA(cudaMemcpyAsync(hops, idx->hops.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    return check_latched(idx);
+}
+
+int rg_search_roargraph(rg_index *idx, const float *queries, uint32_t nq, uint32_t k, uint32_t L_pq, uint32_t *ids,
+                        float *dists, uint32_t *cmps, uint32_t *hops) {
+    return search_host(idx, false, queries, nq, k, L_pq, nullptr, 0, 0, ids, dists, cmps, hops);
+}
+
+int rg_search_bipartite(rg_index *idx, const float *queries, uint32_t nq, uint32_t k, uint32_t L_pq,
+                        const uint32_t *init_ids, uint32_t n_init, uint64_t seed, uint32_t *ids, float *dists,
+                        uint32_t *cmps, uint32_t *hops) {
+    return search_host(idx, true, queries, nq, k, L_pq, init_ids, n_init, seed, ids, dists, cmps, hops);
+}
+
+int rg_search_last_stats(rg_index *idx, uint64_t *total_cmps, uint64_t *total_hops, uint64_t *adj_words) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    RG_CUDA(cudaDeviceSynchronize());
+    unsigned long long st[4];
+    RG_CUDA(cudaMemcpy(st, idx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    if (total_cmps) *total_cmps = st[0];
+    if (total_hops) *total_hops = st[1];
+    if (adj_words) *adj_words = st[2];
+    return RG_OK;
+}
+
+int rg_search_last_launch(rg_index *idx, uint32_t *grid, uint32_t *block, uint32_t *smem_bytes, uint32_t *rows_per_batch) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    if (grid) *grid = idx->last_launch.grid;
+    if (block) *block = idx->last_launch.block;
+    if (smem_bytes) *smem_bytes = idx->last_launch.smem_bytes;
+    if (rows_per_batch) *rows_per_batch = idx->last_launch.rows_per_batch;
+    return RG_OK;
+}
+
+int rg_knn_dev(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
+               int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, void *stream) {
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    return knn_device(d_base, nb, d_queries, nq, dim, K, metric, id_offset, d_ids, d_dists, (cudaStream_t)stream);
+}
+
+int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, uint32_t dim, uint32_t K, int metric,
+           int32_t id_offset, int32_t *ids, float *dists) {
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    if (!base || !queries || !ids || !dists || nb == 0 || dim == 0) { set_error("rg_knn: null/empty argument"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    float *d_b = nullptr, *d_q = nullptr, *d_d = nullptr;
+    int32_t *d_i = nullptr;
+    cudaError_t e = cudaMalloc(&d_b, nb * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_q, nq * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, nq * K * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_i, nq * K * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_b, base, nb * dim * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice);
+    rc = RG_OK;
+    if (e == cudaSuccess) {
+        rc = knn_device(d_b, nb, d_q, nq, dim, K, metric, id_offset, d_i, d_d, nullptr);
+        if (rc == RG_OK) e = cudaDeviceSynchronize();
+        if (rc == RG_OK && e == cudaSuccess) e = cudaMemcpy(ids, d_i, nq * K * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (rc == RG_OK && e == cudaSuccess) e = cudaMemcpy(dists, d_d, nq * K * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    if (d_b) cudaFree(d_b);
+    if (d_q) cudaFree(d_q);
+    if (d_d) cudaFree(d_d);
+    if (d_i) cudaFree(d_i);
+    if (e != cudaSuccess) return cuda_fail(e, "rg_knn");
+    return rc;
+}
+
+int rg_topk_merge_dev(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
+                      float *d_out_dists, uint32_t *d_out_ids, void *stream) {
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    return topk_merge_device(d_in_dists, d_in_ids, G, nq, K, d_out_dists, d_out_ids, (cudaStream_t)stream);
+}
+
+}  // extern "C"

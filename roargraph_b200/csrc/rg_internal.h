@@ -1,0 +1,67 @@
+// Internal declarations shared by the translation units of librg_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/rg_b200.h"
+
+namespace rg {
+
+constexpr uint32_t kExpandedBit = 0x80000000u;  // queue id word: bit 31 = "expanded" flag (neighbor.h:24 `flag`)
+constexpr uint32_t kIdMask = 0x7fffffffu;
+constexpr int kMaxRowsPerBatch = 32;
+constexpr int kCandCap = 96;  // neighbour ids examined per pass (3 per lane)
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define RG_CUDA(call)                                          \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return rg::cuda_fail(_e, #call); \
+    } while (0)
+
+// Launch-time description of one beam-search batch (passed by value to the kernels).
+struct SearchParams {
+    const float *base;        // nd x dim
+    const uint32_t *adj;      // fixed-stride adjacency: row u = [deg, ids...] , adj_stride words   (RoarGraph)
+    const uint64_t *row_off;  // CSR (bipartite graph)
+    const uint32_t *csr_nbrs;
+    uint8_t *tags;            // n_slots x tag_stride visited tags (visited_list_pool.h:8-29, 8-bit epochs)
+    uint32_t *slot_epoch;     // n_slots
+    const float *queries;     // nq x dim
+    const uint32_t *init_ids; // bipartite: nq x n_init (or nullptr -> seeded)
+    uint32_t *out_ids;        // nq x k
+    float *out_dists;         // nq x k
+    uint32_t *out_cmps;       // nq or null
+    uint32_t *out_hops;       // nq or null
+    unsigned long long *stats; // [0]=cmps [1]=hops [2]=adj_words [3]=first error word
+    uint32_t *counter;        // work-queue ticket
+    uint64_t tag_stride;      // bytes per slot (>= nd, 16-aligned)
+    uint64_t seed;
+    uint32_t nd, dim, adj_stride, ep;
+    uint32_t nq, k, L, n_init;
+    uint32_t rows_per_batch;  // R: rows staged per mbarrier round (multiple of 8, <= 32)
+    uint32_t row_stride_smem; // floats; == dim padded so that (stride % 32) == 16 (bank-conflict-free float4 reads)
+    uint32_t warp_smem_bytes; // bytes of dynamic smem per warp
+    int metric_l2;            // 1: squared L2, 0: negative inner product
+};
+
+struct SearchLaunch {
+    uint32_t grid, block, smem_bytes, rows_per_batch, warps_per_cta;
+};
+
+// Computes the launch geometry (and per-warp smem layout fields of `p`) for queue length L.
+int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slots);
+int launch_roargraph(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
+int launch_bipartite(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
+uint32_t max_search_slots(int sm_count);
+
+// exact kNN (rg_knn.cu)
+int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
+               int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s);
+int topk_merge_device(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
+                      float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s);
+
+}  // namespace rg

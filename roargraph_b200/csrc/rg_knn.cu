@@ -1,0 +1,311 @@
+// rg_knn.cu — brute-force training-query x base kNN on sm_100a (exact_knn of the reference's compute_groundtruth,
+// thirdparty/DiskANN/tests/utils/compute_groundtruth.cpp:126-248, paths relative to /root/reference).
+//
+// The reference materialises a 1024 x npoints fp32 distance matrix per query batch with MKL SGEMM and re-streams it
+// through a per-query max-heap (:190-234).  Here the distance tile never leaves the SM: a tiled fp32 GEMM computes
+// 128 x 128 scores per CTA and its epilogue keeps only scores below the query's running K-th best (tau), appending
+// them to a small per-query candidate list; a merge kernel folds the candidates into the sorted top-K and tightens
+// tau.  The base is streamed in chunks of doubling size so that the expected number of survivors per chunk stays ~K.
+// Internal distances as the reference defines them: IP -> -dot (:118-120), L2 -> -2 dot + |p|^2 + |q|^2 (:92-100),
+// COSINE -> L2 on rows divided by their norm (:146-174).  Ties: earlier id wins (strict '>' at :214).
+#include <cfloat>
+#include <cstdio>
+#include <vector>
+
+#include "rg_internal.h"
+
+namespace rg {
+namespace {
+
+constexpr int TQ = 128, TB = 128, TK = 16;
+constexpr int KNN_THREADS = 256;
+
+__device__ __forceinline__ uint32_t f2ord(float f) {  // order-preserving float -> uint
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// squared norms, one warp per row (compute_l2sq, :68-75)
+__global__ void row_sqnorm_kernel(const float *x, uint64_t n, uint32_t dim, float *out) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float *r = x + row * dim;
+    float s = 0.f;
+    for (uint32_t j = lane; j < dim; j += 32) s = fmaf(r[j], r[j], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = s;
+}
+
+// rows / sqrt(norm)  (:146-168; epsilon when the norm is 0)
+__global__ void row_normalize_kernel(const float *x, uint64_t n, uint32_t dim, const float *sq, float *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    float nm = sqrtf(sq[i / dim]);
+    if (nm == 0.f) nm = FLT_EPSILON;
+    out[i] = x[i] / nm;
+}
+
+// Tile GEMM + threshold filter.  scores(q, b) for q in [q0, q0+TQ), b in [b0, b0+TB) of the current base chunk.
+// cand layout: per query `cap` packed (ordered-dist << 32 | id) words.
+__global__ void __launch_bounds__(KNN_THREADS) knn_gemm_filter_kernel(
+    const float *__restrict__ Q, const float *__restrict__ B, uint32_t dim, uint64_t nq, uint64_t chunk_lo,
+    uint64_t chunk_hi, const float *__restrict__ qn, const float *__restrict__ bn, int metric_l2,
+    const float *__restrict__ tau, unsigned long long *__restrict__ cand, uint32_t *__restrict__ cand_cnt, uint32_t cap,
+    uint32_t *overflow) {
+    __shared__ float sQ[TK][TQ + 4];
+    __shared__ float sB[TK][TB + 4];
+    const int tid = threadIdx.x;
+    const uint64_t q0 = (uint64_t)blockIdx.y * TQ;
+    const uint64_t b0 = chunk_lo + (uint64_t)blockIdx.x * TB;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 8 x 8 outputs each (strided by 16)
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // loader mapping: 128 rows x 16 k per tile = 2048 floats = 8 per thread: row = tid >> 1, k-half = (tid & 1) * 8
+    const int lrow = tid >> 1, lk = (tid & 1) * 8;
+    const uint64_t qrow = q0 + lrow, brow = b0 + lrow;
+    const bool qok = qrow < nq, bok = brow < chunk_hi;
+    const float *qp = Q + qrow * dim, *bp = B + brow * dim;
+
+    for (uint32_t k0 = 0; k0 < dim; k0 += TK) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t kk = k0 + lk + j;
+            sQ[lk + j][lrow] = (qok && kk < dim) ? __ldg(qp + kk) : 0.f;
+            sB[lk + j][lrow] = (bok && kk < dim) ? __ldg(bp + kk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            float a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = sQ[k][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = sB[k][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint64_t q = q0 + ty + 16 * i;
+        if (q >= nq) continue;
+        const float t = tau[q];
+        const float qq = metric_l2 ? qn[q] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint64_t b = b0 + tx + 16 * j;
+            if (b >= chunk_hi) continue;
+            float s;
+            if (metric_l2) s = (-2.0f * acc[i][j] + bn[b]) + qq;
+            else s = -acc[i][j];
+            if (s < t) {
+                const uint32_t slot = atomicAdd(cand_cnt + q, 1u);
+                if (slot < cap) cand[q * cap + slot] = ((unsigned long long)f2ord(s) << 32) | (uint32_t)b;
+                else *overflow = 1u;
+            }
+        }
+    }
+}
+
+// Fold candidates into the running sorted top-K of each query (one CTA per query), update tau, reset the counter.
+// top: nq x K packed words ascending (unused tail = ~0ull).
+__global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t K, unsigned long long *__restrict__ cand,
+                                 uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n) {
+    extern __shared__ unsigned long long sk[];
+    const uint64_t q = blockIdx.x;
+    uint32_t n = cand_cnt[q];
+    if (n > cap) n = cap;
+    if (n == 0) return;
+    // smallest power of two holding n + K
+    uint32_t m = 1;
+    while (m < n + K) m <<= 1;
+    if (m > sort_n) m = sort_n;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        unsigned long long v = ~0ull;
+        if (i < n) v = cand[q * cap + i];
+        else if (i < n + K) v = top[q * K + (i - n)];
+        sk[i] = v;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+                const uint32_t lo = 2 * i - (i & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == up) {
+                    sk[lo] = b;
+                    sk[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) top[q * K + i] = sk[i];
+    if (threadIdx.x == 0) {
+        const unsigned long long kth = sk[K - 1];
+        tau[q] = (kth == ~0ull) ? INFINITY : ord2f((uint32_t)(kth >> 32));
+        cand_cnt[q] = 0;
+    }
+}
+
+__global__ void knn_init_kernel(unsigned long long *top, uint64_t n_top, float *tau, uint32_t *cnt, uint64_t nq) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_top) top[i] = ~0ull;
+    if (i < nq) {
+        tau[i] = INFINITY;
+        cnt[i] = 0;
+    }
+}
+
+__global__ void knn_unpack_kernel(const unsigned long long *top, uint64_t n, int32_t id_offset, int32_t *ids, float *dists) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long v = top[i];
+    ids[i] = (v == ~0ull) ? -1 : (int32_t)((uint32_t)v) + id_offset;
+    dists[i] = (v == ~0ull) ? INFINITY : ord2f((uint32_t)(v >> 32));
+}
+
+// merge G sorted lists of K (dist, id) per query: one warp per query, G*K <= 32*32 handled by repeated min-extraction
+__global__ void topk_merge_kernel(const float *in_d, const uint32_t *in_i, uint32_t G, uint64_t nq, uint32_t K, float *out_d,
+                                  uint32_t *out_i) {
+    const uint64_t q = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int lane = threadIdx.x & 31;
+    // lane g owns the head pointer of list g (G <= 32)
+    uint32_t head = 0;
+    const bool own = (uint32_t)lane < G;
+    const float *ld = in_d + ((uint64_t)lane * nq + q) * K;
+    const uint32_t *li = in_i + ((uint64_t)lane * nq + q) * K;
+    for (uint32_t o = 0; o < K; ++o) {
+        unsigned long long key = ~0ull;
+        if (own && head < K) key = ((unsigned long long)f2ord(ld[head]) << 32) | li[head];
+        unsigned long long best = key;
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, s);
+            best = other < best ? other : best;
+        }
+        const uint32_t winners = __ballot_sync(0xffffffffu, own && head < K && key == best);
+        if (winners && lane == __ffs(winners) - 1) {  // keys embed the id, so ties only arise from identical entries
+            out_d[q * K + o] = ld[head];
+            out_i[q * K + o] = li[head];
+            head++;
+        } else if (!winners && lane == 0) {
+            out_d[q * K + o] = INFINITY;
+            out_i[q * K + o] = 0xffffffffu;
+        }
+        __syncwarp();
+    }
+}
+
+struct Scratch {
+    void *p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
+               int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s) {
+    if (!d_base || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
+    if (K == 0 || K > nb) { set_error("rg_knn: K must be in [1, nb]"); return RG_EINVAL; }
+    if (K > 1024) { set_error("rg_knn: K > 1024 not supported"); return RG_EINVAL; }
+    if (nb >= 0x7fffffffull) { set_error("rg_knn: nb must be < 2^31 per call (the reference uses int ids)"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    const bool cosine = metric == RG_METRIC_COSINE;
+    const int metric_l2 = (metric == RG_METRIC_L2 || cosine) ? 1 : 0;
+    if (!metric_l2 && metric != RG_METRIC_INNER_PRODUCT) { set_error("rg_knn: unknown metric"); return RG_EINVAL; }
+
+    const uint32_t cap = std::max<uint32_t>(2048u, 4u * K);
+    uint32_t sort_n = 1;
+    while (sort_n < cap + K) sort_n <<= 1;
+    // query batches so that the candidate lists stay within ~2 GiB
+    const uint64_t qb_max = std::max<uint64_t>(TQ, ((2ull << 30) / (cap * 8ull)) / TQ * TQ);
+
+    Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf;
+    float *bn = nullptr, *qn = nullptr;
+    const float *B = d_base, *Q = d_queries;
+    if (metric_l2) {
+        RG_CUDA(cudaMalloc(&s_bn.p, nb * sizeof(float)));
+        RG_CUDA(cudaMalloc(&s_qn.p, nq * sizeof(float)));
+        bn = (float *)s_bn.p;
+        qn = (float *)s_qn.p;
+        row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(d_base, nb, dim, bn);
+        row_sqnorm_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(d_queries, nq, dim, qn);
+        if (cosine) {
+            RG_CUDA(cudaMalloc(&s_bcopy.p, nb * dim * sizeof(float)));
+            RG_CUDA(cudaMalloc(&s_qcopy.p, nq * dim * sizeof(float)));
+            row_normalize_kernel<<<(unsigned)((nb * dim + 255) / 256), 256, 0, s>>>(d_base, nb, dim, bn, (float *)s_bcopy.p);
+            row_normalize_kernel<<<(unsigned)((nq * dim + 255) / 256), 256, 0, s>>>(d_queries, nq, dim, qn, (float *)s_qcopy.p);
+            B = (const float *)s_bcopy.p;
+            Q = (const float *)s_qcopy.p;
+            row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(B, nb, dim, bn);  // :170-171 recompute
+            row_sqnorm_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(Q, nq, dim, qn);
+        }
+    }
+    const uint64_t qb_alloc = std::min<uint64_t>(nq, qb_max);
+    RG_CUDA(cudaMalloc(&s_top.p, qb_alloc * K * sizeof(unsigned long long)));
+    RG_CUDA(cudaMalloc(&s_cand.p, qb_alloc * cap * sizeof(unsigned long long)));
+    RG_CUDA(cudaMalloc(&s_cnt.p, qb_alloc * sizeof(uint32_t)));
+    RG_CUDA(cudaMalloc(&s_tau.p, qb_alloc * sizeof(float)));
+    RG_CUDA(cudaMalloc(&s_ovf.p, sizeof(uint32_t)));
+    unsigned long long *top = (unsigned long long *)s_top.p, *cand = (unsigned long long *)s_cand.p;
+    uint32_t *cnt = (uint32_t *)s_cnt.p, *ovf = (uint32_t *)s_ovf.p;
+    float *tau = (float *)s_tau.p;
+    RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sort_n * 8)));
+
+    for (uint64_t qs = 0; qs < nq; qs += qb_max) {
+        const uint64_t nqb = std::min<uint64_t>(qb_max, nq - qs);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            // attempt 0: chunks double in size (expected survivors per chunk ~K); attempt 1 (after a candidate-list
+            // overflow): every chunk has at most `cap` rows, which cannot overflow.
+            const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
+            knn_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, s>>>(top, nqb * K, tau, cnt, nqb);
+            RG_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), s));
+            uint64_t lo = 0, csize = cap;
+            while (lo < nb) {
+                const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
+                dim3 grid((unsigned)((hi - lo + TB - 1) / TB), (unsigned)((nqb + TQ - 1) / TQ));
+                knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
+                                                                    bn, metric_l2, tau, cand, cnt, cap, ovf);
+                knn_merge_kernel<<<(unsigned)nqb, 256, sort_n * 8, s>>>(top, K, cand, cnt, cap, tau, sort_n);
+                if (attempt == 0 && lo > 0) csize = std::min<uint64_t>(csize * 2, 1ull << 22);
+                lo = hi;
+            }
+            RG_CUDA(cudaGetLastError());
+            uint32_t h_ovf = 0;
+            RG_CUDA(cudaMemcpyAsync(&h_ovf, ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            RG_CUDA(cudaStreamSynchronize(s));
+            if (!h_ovf) break;
+            if (attempt == 1) { set_error("rg_knn: candidate overflow in safe mode (internal error)"); return RG_ENOMEM; }
+        }
+        knn_unpack_kernel<<<(unsigned)((nqb * K + 255) / 256), 256, 0, s>>>(top, nqb * K, id_offset, d_ids + qs * K, d_dists + qs * K);
+    }
+    RG_CUDA(cudaGetLastError());
+    RG_CUDA(cudaStreamSynchronize(s));
+    return RG_OK;
+}
+
+int topk_merge_device(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
+                      float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s) {
+    if (!d_in_dists || !d_in_ids || !d_out_dists || !d_out_ids) { set_error("rg_topk_merge: null buffer"); return RG_EINVAL; }
+    if (G == 0 || G > 32) { set_error("rg_topk_merge: G must be in [1, 32]"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    topk_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>(d_in_dists, d_in_ids, G, nq, K, d_out_dists, d_out_ids);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+}  // namespace rg

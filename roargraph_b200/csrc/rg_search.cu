@@ -1,0 +1,510 @@
+// rg_search.cu — batched greedy beam search on sm_100a: one warp per query.
+//
+// Replaces the per-query loop of IndexBipartite::SearchRoarGraph (src/index_bipartite.cpp:2311-2420) and
+// IndexBipartite::SearchBipartiteGraph (:282-356) of the reference (paths relative to /root/reference) for a
+// whole query batch.  Results are bit-identical to the reference's CPU path: same ids, same fp32 distances,
+// same cmps / hops.
+//
+// Design:
+//   * persistent CTAs, each warp pulls query ids from an atomic ticket (the reference's schedule(dynamic,1));
+//   * candidate queue (NeighborPriorityQueue, neighbor.h:138-223) = sorted (dist,id|flag) arrays in shared memory,
+//     maintained by warp-cooperative 32-ary search + parallel shift;
+//   * visited set (VisitedList, visited_list_pool.h:8-29) = exact per-warp tag array in HBM with 8-bit epochs;
+//   * neighbour rows are gathered HBM -> shared memory with one cp.async.bulk (TMA 1-D bulk copy, UBLKCP) per row,
+//     completion tracked per group of 8 rows on an mbarrier, so every row of a hop is in flight at once;
+//   * distances reproduce the reference's AVX-512 rounding order exactly (distance.h:39-89,179-225 as compiled):
+//     4 lanes per row, each owning 4 of the 16 virtual SIMD lanes; unfused mul+add in the 16-wide loop,
+//     fma in the 8-wide tail, pairwise folds by shuffles.
+#include <cstdio>
+#include <cstdlib>
+
+#include "rg_internal.h"
+
+namespace rg {
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// One row HBM -> shared memory through the bulk-copy (TMA) engine; completes `bytes` on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ bool nbr_less(float d1, uint32_t i1, float d2, uint32_t i2) {  // neighbor.h:29-31
+    return d1 < d2 || (d1 == d2 && i1 < i2);
+}
+
+// Distance::compare as the reference computes it (distance.h:39-89 / :179-225 compiled with -Ofast -march=native;
+// DESIGN.md documents the rounding order).  `t` = lane & 3 owns virtual SIMD lanes 4t..4t+3 of one row;
+// the result is valid in the lane with t == 0.  dim % 8 == 0, so only the 16-wide loop and the 8-wide block exist.
+template <bool kL2>
+__device__ __forceinline__ float row_distance(const float *row, const float *q, int n16, bool has8, int t) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(row) + t;
+    const float4 *q4 = reinterpret_cast<const float4 *>(q) + t;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < n16; ++c) {
+        const float4 a = r4[4 * c];
+        const float4 b = q4[4 * c];
+        if (kL2) {
+            const float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z),
+                        d3 = __fsub_rn(a.w, b.w);
+            s0 = __fadd_rn(s0, __fmul_rn(d0, d0));
+            s1 = __fadd_rn(s1, __fmul_rn(d1, d1));
+            s2 = __fadd_rn(s2, __fmul_rn(d2, d2));
+            s3 = __fadd_rn(s3, __fmul_rn(d3, d3));
+        } else {
+            s0 = __fadd_rn(s0, __fmul_rn(a.x, b.x));
+            s1 = __fadd_rn(s1, __fmul_rn(a.y, b.y));
+            s2 = __fadd_rn(s2, __fmul_rn(a.z, b.z));
+            s3 = __fadd_rn(s3, __fmul_rn(a.w, b.w));
+        }
+    }
+    // t[l] = s[l+8] + s[l]  (virtual lanes l+8 live two threads up)
+    float t0 = __fadd_rn(__shfl_down_sync(kFull, s0, 2, 4), s0);
+    float t1 = __fadd_rn(__shfl_down_sync(kFull, s1, 2, 4), s1);
+    float t2 = __fadd_rn(__shfl_down_sync(kFull, s2, 2, 4), s2);
+    float t3 = __fadd_rn(__shfl_down_sync(kFull, s3, 2, 4), s3);
+    if (has8 && t < 2) {
+        const float4 a = r4[4 * n16];
+        const float4 b = q4[4 * n16];
+        if (kL2) {
+            const float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y), d2 = __fsub_rn(a.z, b.z),
+                        d3 = __fsub_rn(a.w, b.w);
+            t0 = __fmaf_rn(d0, d0, t0);
+            t1 = __fmaf_rn(d1, d1, t1);
+            t2 = __fmaf_rn(d2, d2, t2);
+            t3 = __fmaf_rn(d3, d3, t3);
+        } else {
+            t0 = __fmaf_rn(a.x, b.x, t0);
+            t1 = __fmaf_rn(a.y, b.y, t1);
+            t2 = __fmaf_rn(a.z, b.z, t2);
+            t3 = __fmaf_rn(a.w, b.w, t3);
+        }
+    }
+    // u[l] = t[l+4] + t[l]
+    const float u0 = __fadd_rn(__shfl_down_sync(kFull, t0, 1, 4), t0);
+    const float u1 = __fadd_rn(__shfl_down_sync(kFull, t1, 1, 4), t1);
+    const float u2 = __fadd_rn(__shfl_down_sync(kFull, t2, 1, 4), t2);
+    const float u3 = __fadd_rn(__shfl_down_sync(kFull, t3, 1, 4), t3);
+    const float res = __fadd_rn(__fadd_rn(u0, u1), __fadd_rn(u2, u3));  // two vhaddps
+    return kL2 ? res : -res;
+}
+
+// Per-warp state of one query.
+struct WarpCtx {
+    float *q;          // dim
+    float *rows;       // R x rstride
+    float *qd;         // L   queue distances, ascending
+    uint32_t *qi;      // L   queue ids | kExpandedBit
+    uint32_t *cand;    // kCandCap
+    uint32_t bar0;     // shared address of mbarrier[0] (4 barriers, one per group of 8 rows)
+    uint32_t rows_u32; // shared address of rows
+    uint32_t size, cur, phase;
+    int lane;
+};
+
+// NeighborPriorityQueue::insert (neighbor.h:150-183), warp-cooperative.  All lanes pass the same (cd, cid).
+// Returns true when the candidate entered the queue.
+__device__ __forceinline__ bool queue_insert(WarpCtx &w, uint32_t L, float cd, uint32_t cid) {
+    const int lane = w.lane;
+    float *qd = w.qd;
+    uint32_t *qi = w.qi;
+    if (w.size == L) {  // :151 full and last < nbr  (an exact duplicate of `last` is caught below)
+        const float ld = qd[L - 1];
+        const uint32_t li = qi[L - 1] & kIdMask;
+        if (!nbr_less(cd, cid, ld, li)) return false;
+    }
+    // lo = number of entries e with !(c < e), found by 32-ary search (entries are sorted)
+    uint32_t lo = 0, len = w.size;
+    while (len > 32) {
+        const uint32_t step = (len + 31) >> 5;
+        const uint32_t end = lo + len;
+        const uint32_t idx = min(lo + (lane + 1) * step, end) - 1;
+        const float ed = qd[idx];
+        const uint32_t ei = qi[idx] & kIdMask;
+        const bool le = !nbr_less(cd, cid, ed, ei);
+        const uint32_t nle = __popc(__ballot_sync(kFull, le));
+        if (nle == 32) {
+            lo = end;
+            len = 0;
+        } else {
+            const uint32_t new_lo = (nle == 0) ? lo : min(lo + nle * step, end);
+            const uint32_t p_hi = min(lo + (nle + 1) * step, end) - 1;  // first probe known to be > c
+            lo = new_lo;
+            len = p_hi - new_lo;
+        }
+    }
+    {
+        const uint32_t idx = lo + lane;
+        bool le = false;
+        if ((uint32_t)lane < len) le = !nbr_less(cd, cid, qd[idx], qi[idx] & kIdMask);
+        lo += __popc(__ballot_sync(kFull, le));
+    }
+    // :161 same id met on the search path == exact duplicate sits right below the insertion point
+    if (lo > 0 && (qi[lo - 1] & kIdMask) == cid && qd[lo - 1] == cd) return false;
+    const uint32_t newsize = min(w.size + 1, L);
+    // :169 memmove of the tail one slot up (the last entry falls off when full)
+    for (int hi = (int)newsize - 1; hi > (int)lo; hi -= 32) {
+        const int j = hi - lane;
+        const bool act = j > (int)lo;
+        float td = 0.f;
+        uint32_t ti = 0;
+        if (act) {
+            td = qd[j - 1];
+            ti = qi[j - 1];
+        }
+        __syncwarp();
+        if (act) {
+            qd[j] = td;
+            qi[j] = ti;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        qd[lo] = cd;
+        qi[lo] = cid;  // flag = false (:174)
+    }
+    __syncwarp();
+    w.size = newsize;
+    if (lo < w.cur) w.cur = lo;  // :180
+    return true;
+}
+
+// NeighborPriorityQueue::closest_unexpanded (neighbor.h:185-192): flag entry `cur`, advance to the next unflagged one.
+__device__ __forceinline__ uint32_t queue_pop(WarpCtx &w) {
+    const uint32_t u = w.qi[w.cur] & kIdMask;
+    __syncwarp();
+    if (w.lane == 0) w.qi[w.cur] = u | kExpandedBit;
+    __syncwarp();
+    uint32_t c = w.cur + 1;
+    for (;;) {
+        const uint32_t j = c + w.lane;
+        const bool stop = (j >= w.size) || !(w.qi[j] & kExpandedBit);
+        const uint32_t m = __ballot_sync(kFull, stop);
+        if (m) {
+            c += __ffs(m) - 1;
+            break;
+        }
+        c += 32;
+    }
+    w.cur = min(c, w.size);
+    return u;
+}
+
+// Evaluate cand[0..n) against the query and insert them: gather rows with bulk copies, 8 rows per mbarrier group.
+template <bool kL2>
+__device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj) {
+    const int lane = w.lane;
+    const uint32_t R = p.rows_per_batch;
+    const uint32_t row_bytes = p.dim * 4u;
+    const uint32_t rstride = p.row_stride_smem;
+    const int n16 = p.dim >> 4;
+    const bool has8 = (p.dim & 8u) != 0;
+    const int t = lane & 3;
+    for (uint32_t b0 = 0; b0 < n; b0 += R) {
+        const uint32_t nb = min(R, n - b0);
+        const uint32_t ngroups = (nb + 7) >> 3;
+        if ((uint32_t)lane < ngroups) mbar_expect_tx(w.bar0 + 8u * lane, min(8u, nb - 8u * lane) * row_bytes);
+        if ((uint32_t)lane < nb) {
+            const uint32_t id = w.cand[b0 + lane];
+            bulk_g2s(w.rows_u32 + lane * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * (lane >> 3));
+        }
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            mbar_wait(w.bar0 + 8u * g, (w.phase >> g) & 1u);
+            w.phase ^= (1u << g);
+            const uint32_t r = 8u * g + (lane >> 2);
+            const bool valid = r < nb;
+            const float d = row_distance<kL2>(w.rows + (size_t)(valid ? r : 0) * rstride, w.q, n16, has8, t);
+            const uint32_t id = valid ? w.cand[b0 + r] : 0u;
+            bool pass = valid && t == 0;
+            if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
+            uint32_t m = __ballot_sync(kFull, pass);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cd = __shfl_sync(kFull, d, src);
+                const uint32_t cid = __shfl_sync(kFull, id, src);
+                const bool in = queue_insert(w, p.L, cd, cid);
+                if (in && prefetch_adj) {
+                    // the candidate sits in the top-L now and will very likely be expanded (hops ~= L):
+                    // pull its adjacency row towards L2 so the dependent read at expansion time is short.
+                    const char *a = reinterpret_cast<const char *>(p.adj + (size_t)cid * p.adj_stride);
+                    const uint32_t bytes = p.adj_stride * 4u;
+                    if ((uint32_t)lane * 32u < bytes) prefetch_l2(a + lane * 32u);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Visited filter (visited_list_pool.h / src/index_bipartite.cpp:2378-2386): appends the not-yet-visited ids of
+// list[0..cnt) to cand[ncand..] and tags them.  Up to kCandCap ids per call; lists are duplicate-free (deduplicated at upload).
+__device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, uint8_t epoch, const uint32_t *list,
+                                                     uint32_t cnt, uint32_t ncand) {
+    const int lane = w.lane;
+    uint32_t id[3];
+    uint8_t tg[3];
+    bool valid[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint32_t i = j * 32 + lane;
+        valid[j] = i < cnt;
+        id[j] = valid[j] ? __ldg(list + i) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tg[j] = valid[j] ? __ldcg(tags + id[j]) : epoch;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const bool fresh = valid[j] && tg[j] != epoch;
+        if (fresh) __stcg(tags + id[j], epoch);
+        const uint32_t m = __ballot_sync(kFull, fresh);
+        if (fresh) w.cand[ncand + __popc(m & ((1u << lane) - 1u))] = id[j];
+        ncand += __popc(m);
+    }
+    __syncwarp();
+    return ncand;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+template <bool kL2, bool kBipartite>
+__global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    uint8_t *ws = smem_raw + (size_t)warp * p.warp_smem_bytes;
+
+    WarpCtx w;
+    w.lane = lane;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ws);  // 4 x 8 B, padded to 64 B
+    w.q = reinterpret_cast<float *>(ws + 64);
+    w.rows = w.q + p.dim;
+    w.qd = w.rows + (size_t)p.rows_per_batch * p.row_stride_smem;
+    w.qi = reinterpret_cast<uint32_t *>(w.qd + p.L);
+    w.cand = w.qi + p.L;
+    w.bar0 = smem_u32(bars);
+    w.rows_u32 = smem_u32(w.rows);
+    w.phase = 0;
+    if (lane < 4) mbar_init(w.bar0 + 8u * lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    const uint32_t slot = blockIdx.x * warps_per_cta + warp;
+    uint8_t *tags = p.tags + (size_t)slot * p.tag_stride;
+    uint32_t epoch = p.slot_epoch[slot];
+    unsigned long long acc_cmps = 0, acc_hops = 0, acc_adj = 0;
+    const bool prefetch_adj = !kBipartite && p.n_init != 0;  // n_init doubles as the prefetch switch for RoarGraph
+
+    for (;;) {
+        uint32_t qidx = 0;
+        if (lane == 0) qidx = atomicAdd(p.counter, 1u);
+        qidx = __shfl_sync(kFull, qidx, 0);
+        if (qidx >= p.nq) break;
+
+        // VisitedList::reset (visited_list_pool.h:20-26): bump the tag, clear the array when it wraps
+        if (++epoch > 255u) {
+            uint4 z = make_uint4(0, 0, 0, 0);
+            for (uint64_t i = (uint64_t)lane * 16u; i < p.tag_stride; i += 512u) *reinterpret_cast<uint4 *>(tags + i) = z;
+            epoch = 1;
+            __threadfence_block();
+        }
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(p.queries + (size_t)qidx * p.dim);
+            float4 *dst = reinterpret_cast<float4 *>(w.q);
+            for (uint32_t i = lane; i < (p.dim >> 2); i += 32) dst[i] = __ldg(src + i);
+        }
+        w.size = 0;
+        w.cur = 0;
+        __syncwarp();
+
+        uint32_t cmps = 0, hops = 0, adjw = 0;
+        // entry points (:2323-2353 / :287-310)
+        if (!kBipartite) {
+            if (lane == 0) w.cand[0] = p.ep;  // evaluated + inserted, NOT marked visited (:2349 is commented out)
+            __syncwarp();
+            evaluate_candidates<kL2>(w, p, 1, false);
+        } else {
+            for (uint32_t i = lane; i < p.n_init; i += 32) {
+                uint32_t id;
+                if (p.init_ids) id = p.init_ids[(size_t)qidx * p.n_init + i];
+                else id = (uint32_t)(splitmix64(p.seed + (uint64_t)qidx * p.n_init + i) % p.nd);
+                w.cand[i] = id;
+                __stcg(tags + id, (uint8_t)epoch);  // :306 entry points are marked visited
+            }
+            __syncwarp();
+            evaluate_candidates<kL2>(w, p, p.n_init, false);
+        }
+
+        while (w.cur < w.size) {  // has_unexpanded_node
+            const uint32_t u = queue_pop(w);
+            ++hops;
+            if (!kBipartite) {
+                const uint32_t *arow = p.adj + (size_t)u * p.adj_stride;
+                const uint32_t deg = __ldg(arow);
+                adjw += deg;
+                for (uint32_t off = 0; off < deg; off += kCandCap) {
+                    const uint32_t n = filter_unvisited(w, tags, (uint8_t)epoch, arow + 1 + off, min(deg - off, (uint32_t)kCandCap), 0);
+                    cmps += n;
+                    if (n) evaluate_candidates<kL2>(w, p, n, prefetch_adj);
+                }
+            } else {
+                // two-hop expansion through the query nodes (:324-341); hops++ precedes the empty-adjacency skip (:320-323)
+                const uint64_t b = p.row_off[u], e = p.row_off[u + 1];
+                adjw += (uint32_t)(e - b);
+                uint32_t ncand = 0;
+                for (uint64_t j = b; j < e; ++j) {
+                    const uint32_t nbr = __ldg(p.csr_nbrs + j);
+                    const uint64_t b2 = p.row_off[nbr], e2 = p.row_off[nbr + 1];
+                    adjw += (uint32_t)(e2 - b2);
+                    for (uint64_t off = b2; off < e2; off += 32) {
+                        if (ncand + 32 > (uint32_t)kCandCap) {
+                            cmps += ncand;
+                            evaluate_candidates<kL2>(w, p, ncand, false);
+                            ncand = 0;
+                        }
+                        ncand = filter_unvisited(w, tags, (uint8_t)epoch, p.csr_nbrs + off, (uint32_t)min((uint64_t)32, e2 - off), ncand);
+                    }
+                }
+                if (ncand) {
+                    cmps += ncand;
+                    evaluate_candidates<kL2>(w, p, ncand, false);
+                }
+            }
+        }
+
+        // :2408-2418
+        if (w.size < p.k && lane == 0) atomicCAS(p.stats + 3, 0ull, ((unsigned long long)w.size << 32) | 1ull);
+        for (uint32_t i = lane; i < p.k; i += 32) {
+            const bool ok = i < w.size;
+            p.out_ids[(size_t)qidx * p.k + i] = ok ? (w.qi[i] & kIdMask) : 0xffffffffu;
+            p.out_dists[(size_t)qidx * p.k + i] = ok ? w.qd[i] : 0.f;
+        }
+        if (lane == 0) {
+            if (p.out_cmps) p.out_cmps[qidx] = cmps;
+            if (p.out_hops) p.out_hops[qidx] = hops;
+        }
+        acc_cmps += cmps;
+        acc_hops += hops;
+        acc_adj += adjw;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        p.slot_epoch[slot] = epoch;
+        if (acc_hops) {
+            atomicAdd(p.stats + 0, acc_cmps);
+            atomicAdd(p.stats + 1, acc_hops);
+            atomicAdd(p.stats + 2, acc_adj);
+        }
+    }
+}
+
+uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+constexpr uint32_t kMaxSmemPerCta = 227u * 1024u;
+
+uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L) {
+    uint32_t b = 64 + dim * 4 + R * rstride * 4 + L * 8 + kCandCap * 4;
+    return (b + 127u) & ~127u;
+}
+
+template <bool kL2, bool kBip>
+int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    auto kern = beam_search_kernel<kL2, kBip>;
+    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+    RG_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), s));
+    RG_CUDA(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s));
+    kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+}  // namespace
+
+uint32_t max_search_slots(int sm_count) { return (uint32_t)sm_count * 16u; }
+
+int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slots) {
+    const uint32_t dim = p.dim;
+    p.row_stride_smem = dim + ((16u + 32u - (dim & 31u)) & 31u);  // stride % 32 == 16 -> conflict-free float4 reads
+    uint32_t R = env_u32("RG_ROWS_PER_BATCH", 16);
+    if (R < 8) R = 8;
+    if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
+    R &= ~7u;
+    uint32_t warps = env_u32("RG_WARPS_PER_CTA", 4);
+    if (warps < 1) warps = 1;
+    if (warps > 4) warps = 4;
+    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
+    while (warps * wb > kMaxSmemPerCta && R > 8) {
+        R -= 8;
+        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
+    }
+    while (warps > 1 && warps * wb > kMaxSmemPerCta) warps >>= 1;
+    if (warps * wb > kMaxSmemPerCta) {
+        set_error("L_pq / dim too large for one warp's shared-memory working set");
+        return RG_EINVAL;
+    }
+    uint32_t ctas = kMaxSmemPerCta / (warps * wb + 1024u);
+    if (ctas < 1) ctas = 1;
+    const uint32_t max_ctas = 16u / warps;
+    if (ctas > max_ctas) ctas = max_ctas;
+    const uint32_t env_ctas = env_u32("RG_CTAS_PER_SM", 0);
+    if (env_ctas && env_ctas < ctas) ctas = env_ctas;
+    uint32_t grid = (uint32_t)sm_count * ctas;
+    const uint32_t need = (p.nq + warps - 1) / warps;
+    if (grid > need) grid = need;
+    if (grid * warps > max_slots) grid = max_slots / warps;
+    if (grid < 1) grid = 1;
+    p.rows_per_batch = R;
+    p.warp_smem_bytes = wb;
+    l.grid = grid;
+    l.block = warps * 32;
+    l.smem_bytes = warps * wb;
+    l.rows_per_batch = R;
+    l.warps_per_cta = warps;
+    return RG_OK;
+}
+
+int launch_roargraph(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    return p.metric_l2 ? launch_t<true, false>(p, l, s) : launch_t<false, false>(p, l, s);
+}
+int launch_bipartite(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    return p.metric_l2 ? launch_t<true, true>(p, l, s) : launch_t<false, true>(p, l, s);
+}
+
+}  // namespace rg

@@ -1,0 +1,166 @@
+"""GPU parity tests for the beam-search kernels, through the C-ABI (librg_b200.so) against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import roargraph_b200 as rg
+from gpu_helpers import assert_same_search, bipartite_from_knn, bits, build_reference_case, random_graph
+from oracle.oracle import have_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_parity(oracle, golden):
+    """Committed reference outputs: ids, distance bits, cmps, hops identical at every stored L_pq."""
+    base, queries = golden.normalised(oracle)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    for L in golden.Ls:
+        want = {k: golden.z[f"{k}_L{L}"] for k in ("ids", "dists", "cmps", "hops")}
+        assert_same_search(idx.search(queries, golden.k, L), want, f"{golden.name} L={L}")
+    idx.close()
+
+
+@pytest.mark.parametrize("L", [10, 11, 33, 64, 257, 2000])
+def test_oracle_parity_various_L(oracle, golden, L):
+    base, queries = golden.normalised(oracle)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    for k in (1, 10):
+        want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries, k, L)
+        assert_same_search(idx.search(queries, k, L), want, f"{golden.name} L={L} k={k}")
+    # k == L
+    want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries[:7], L, L)
+    assert_same_search(idx.search(queries[:7], L, L), want, "k==L")
+    idx.close()
+
+
+@pytest.mark.parametrize("dim,metric,deg", [(8, "ip", (0, 5)), (16, "l2", (1, 40)), (200, "ip", (20, 70)),
+                                            (512, "ip", (5, 33)), (24, "l2", (90, 150))])
+def test_random_graphs_with_duplicates_selfloops_and_big_degrees(oracle, dim, metric, deg):
+    """Adversarial graphs: repeated ids inside rows, self loops, empty rows, rows longer than one 96-id pass."""
+    rng = np.random.default_rng(dim)
+    nd = 3000
+    base = rng.standard_normal((nd, dim)).astype(np.float32)
+    queries = rng.standard_normal((37, dim)).astype(np.float32)
+    row_off, nbrs = random_graph(rng, nd, deg[0], deg[1], dup_frac=0.3, self_loops=True, zero_frac=0.05)
+    ep = 5
+    idx = rg.RoarIndex(base, metric)
+    idx.set_graph(ep, row_off, nbrs)
+    for L in (10, 100):
+        want = oracle.search_roargraph(base, row_off, nbrs, ep, metric, queries, 1, L)
+        ok = want["status"] == 0
+        if not ok.all():
+            with pytest.raises(rg.RgError) as e:
+                idx.search(queries, 1, L)
+            assert e.value.code == rg.RG_ENOTENOUGH
+            continue
+        assert_same_search(idx.search(queries, 1, L), want, f"random dim={dim} L={L}")
+    idx.close()
+
+
+def test_errors(oracle):
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((100, 16)).astype(np.float32)
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    with pytest.raises(rg.RgError) as e:
+        rg.RoarIndex(rng.standard_normal((10, 12)).astype(np.float32), "ip")  # dim not padded to x8
+    assert e.value.code == rg.RG_EINVAL
+    idx = rg.RoarIndex(base, "ip")
+    with pytest.raises(rg.RgError) as e:
+        idx.search(q, 1, 10)  # graph not set
+    assert e.value.code == rg.RG_ESTATE
+    row_off = np.zeros(101, dtype=np.uint64)
+    idx.set_graph(0, row_off, np.zeros(0, np.uint32))
+    with pytest.raises(rg.RgError) as e:
+        idx.search(q, 11, 10)  # k > L_pq (CLI: "L_pq must greater or equal than k")
+    assert e.value.code == rg.RG_EINVAL
+    with pytest.raises(rg.RgError) as e:
+        idx.search(q, 5, 10)  # edge-less graph: only the entry point is found
+    assert e.value.code == rg.RG_ENOTENOUGH and "not enough results: 1" in str(e.value)
+    ids, dists, cmps, hops = idx.search(q, 1, 10)
+    assert (ids == 0).all() and (cmps == 0).all() and (hops == 1).all()
+    with pytest.raises(rg.RgError):
+        idx.set_graph(100, row_off, np.zeros(0, np.uint32))  # entry point out of range
+    idx.close()
+
+
+def test_device_pointer_entry_and_stats(oracle, golden):
+    import torch
+    base, queries = golden.normalised(oracle)
+    d_base = torch.from_numpy(base).cuda()
+    idx = rg.RoarIndex(d_base, golden.metric)
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    L, k = 32, golden.k
+    d_q = torch.from_numpy(queries).cuda()
+    nq = d_q.shape[0]
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    d_dists = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    d_cmps = torch.empty(nq, dtype=torch.int32, device="cuda")
+    d_hops = torch.empty(nq, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream()
+    idx.search_dev(d_q, k, L, d_ids, d_dists, d_cmps, d_hops, stream=s)
+    idx.check(s)
+    want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries, k, L)
+    got = (d_ids.cpu().numpy().view(np.uint32), d_dists.cpu().numpy(), d_cmps.cpu().numpy().view(np.uint32),
+           d_hops.cpu().numpy().view(np.uint32))
+    assert_same_search(got, want, "device-pointer entry")
+    st = idx.last_stats()
+    assert st["cmps"] == int(want["cmps"].sum()) and st["hops"] == int(want["hops"].sum())
+    assert st["adj_words"] == int(want["adj_words"].sum())
+    idx.close()
+
+
+def test_visited_epoch_wrap(oracle, monkeypatch):
+    """> 255 queries through the same warp slot: the 8-bit visited epoch wraps and the tag array is cleared
+    (VisitedList::reset, visited_list_pool.h:20-26)."""
+    from conftest import GoldenCase
+    g = GoldenCase("ip_d40")
+    monkeypatch.setenv("RG_CTAS_PER_SM", "1")
+    monkeypatch.setenv("RG_WARPS_PER_CTA", "1")
+    base, queries = g.base, g.queries
+    reps = (rg.sm_count() * 300) // queries.shape[0] + 1
+    big = np.ascontiguousarray(np.tile(queries, (reps, 1)))
+    idx = rg.RoarIndex(base, "ip")
+    idx.set_graph(g.ep, g.row_off, g.nbrs)
+    ids, dists, cmps, hops = idx.search(big, g.k, 10)
+    want = {k: np.tile(g.z[f"{k}_L10"], (reps, 1) if g.z[f"{k}_L10"].ndim == 2 else reps) for k in ("ids", "dists", "cmps", "hops")}
+    assert_same_search((ids, dists, cmps, hops), want, "epoch wrap")
+    idx.close()
+
+
+def test_bipartite_parity(oracle, golden):
+    """SearchBipartiteGraph with injected entry points vs the oracle restatement (src/index_bipartite.cpp:282-356)."""
+    base, queries = golden.normalised(oracle)
+    nd = base.shape[0]
+    row_off, nbrs = bipartite_from_knn(golden.z["train_knn_ids"], nd, 12)
+    rng = np.random.default_rng(1)
+    init = rng.integers(0, nd, (queries.shape[0], 10)).astype(np.uint32)
+    init[0, 1] = init[0, 0]  # repeated entry point
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_bipartite(row_off, nbrs)
+    for L in (10, 50, 300):
+        want = oracle.search_bipartite(base, row_off, nbrs, init, golden.metric, queries, golden.k, L)
+        assert want["nfail"] == 0
+        assert_same_search(idx.search_bipartite(queries, golden.k, L, init_ids=init), want, f"bipartite L={L}")
+    # seeded entry points: deterministic, in range, and equal to running with those ids injected
+    a = idx.search_bipartite(queries, golden.k, 50, seed=42)
+    b = idx.search_bipartite(queries, golden.k, 50, seed=42)
+    assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
+    idx.close()
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not available")
+@pytest.mark.parametrize("nb,dim,metric", [(60000, 200, "ip"), (30000, 512, "cosine"), (30000, 96, "l2")])
+def test_live_reference_parity_at_scale(nb, dim, metric):
+    """Index built by the reference's own BuildRoarGraph on the box; GPU search vs the reference's SearchRoarGraph
+    (compiled unmodified) on 500 queries across the L_pq sweep's range."""
+    c = build_reference_case(nb, nb // 2, 500, dim, metric)
+    idx = rg.RoarIndex(c["base"], metric)
+    idx.set_graph(c["ep"], c["row_off"], c["nbrs"])
+    for L in (10, 20, 50, 100, 200, 500, 1000, 2000):
+        want = c["R"].search_roargraph(c["h"], c["queries"], 10, L, c["threads"])
+        assert_same_search(idx.search(c["queries"], 10, L), want, f"{metric} nb={nb} L={L}")
+    c["R"].index_free(c["h"])
+    idx.close()
