@@ -187,6 +187,27 @@ class Reference:
         self.lib.ref_index_free(h)
 
 
+def run_ref_build_roargraph(base_fbin, train_fbin, knn_file, out_index, dist, M_sq, M_pjbp, L_pjpq, threads, quiet=True,
+                            retries=3):
+    """Run the reference's own build CLI (tests/test_build_roargraph.cpp compiled unmodified) in a SUBPROCESS.
+    Its multi-threaded build reads neighbour vectors that other threads are growing ("benign-by-design"
+    races, e.g. src/index_bipartite.cpp:1325 vs :1365); under 16 threads that occasionally corrupts the heap, so the
+    build is isolated from the test process and retried if it dies."""
+    exe = os.path.join(HERE, "_ref", "ref_test_build_roargraph")
+    cmd = [exe, "--data_type", "float", "--dist", dist, "--base_data_path", base_fbin, "--sampled_query_data_path",
+           train_fbin, "--projection_index_save_path", out_index, "--learn_base_nn_path", knn_file, "--M_sq", str(M_sq),
+           "--M_pjbp", str(M_pjbp), "--L_pjpq", str(L_pjpq), "-T", str(threads)]
+    last = None
+    for _ in range(retries):
+        if os.path.exists(out_index):
+            os.remove(out_index)
+        p = subprocess.run(cmd, stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.STDOUT if quiet else None)
+        if p.returncode == 0 and os.path.exists(out_index):
+            return
+        last = p.returncode
+    raise RuntimeError(f"reference build CLI failed (rc={last})")
+
+
 def run_ref_compute_groundtruth(base_fbin, query_fbin, gt_file, K, dist_fn, quiet=True):
     """Run the reference's compute_groundtruth binary (compiled unmodified; MKL via torch's libtorch_cpu.so)."""
     exe = os.path.join(HERE, "_ref", "ref_compute_groundtruth")

@@ -60,18 +60,20 @@ def build_reference_case(nb, ntrain, ntest, dim, metric, M_sq=100, M_pjbp=35, L_
     """Synthetic data -> kNN on the GPU (rg.knn) -> index built by the REFERENCE's BuildRoarGraph (oracle/_ref).
     Returns dict(base, queries (padded/normalised as the reference's search sees them), ep, row_off, nbrs, ref handle)."""
     import roargraph_b200 as rg
-    from oracle.oracle import Reference
+    from oracle.oracle import Reference, run_ref_build_roargraph
     R = Reference()
     threads = threads or R.num_procs()
     base, train, test = synth.make_numpy(nb, ntrain, ntest, dim, seed=seed)
     d = tempfile.mkdtemp(prefix="rgcase_")
     bf, gf, kf = os.path.join(d, "base.fbin"), os.path.join(d, "index.rg"), os.path.join(d, "train.gt")
+    tf = os.path.join(d, "train.fbin")
     F.write_fbin(bf, base)
+    F.write_fbin(tf, train)
     ids, dists = rg.knn(base, train, M_sq, metric)
     if metric == "ip":
         dists = -dists
     F.write_truthset(kf, ids.astype(np.uint32), dists)
-    R.build_roargraph(bf, kf, gf, metric, M_sq, M_pjbp, L_pjpq, threads)
+    run_ref_build_roargraph(bf, tf, kf, gf, metric, M_sq, M_pjbp, L_pjpq, threads)
     ep, row_off, nbrs = F.read_projection_index(gf)
     pdim = (dim + 7) // 8 * 8
     h = R.index_load(bf, gf, metric, pdim, threads)
