@@ -66,6 +66,19 @@ int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_
 
 int rg_index_destroy(rg_index *idx);
 
+/* ---- BuildRoarGraph on the device ----------------------------------------------
+ * knn_ids: nsq x knn_stride base ids, row i = the nearest base rows of training query i in ascending distance — the
+ * content of the learn-base kNN file read by LoadLearnBaseKNN (src/index_bipartite.cpp:2622-2642); the first M_sq of
+ * every row are used (LinkProjection :1063-1067).  knn_on_device != 0: device pointer.  M_pjbp / L_pjpq as in
+ * tests/test_build_roargraph.cpp:52-60.  n_rounds = number of bulk-synchronous rounds of the connectivity-enhancement
+ * phase (0 = automatic).  Replaces BuildRoarGraph (:143-233); the result is deterministic, and statistically — not
+ * id-for-id — equivalent to the reference's thread-timing-dependent build.  Sets the index's graph and entry point. */
+int rg_index_build_roargraph(rg_index *idx, const uint32_t *knn_ids, int knn_on_device, uint64_t nsq,
+                             uint32_t knn_stride, uint32_t M_sq, uint32_t M_pjbp, uint32_t L_pjpq, uint32_t n_rounds);
+/* Export the index's projection graph (set or built) as host CSR: what SaveProjectionGraph writes (:2606-2619). */
+int rg_index_graph_size(rg_index *idx, uint64_t *nnz, uint32_t *ep, uint32_t *max_degree);
+int rg_index_get_graph(rg_index *idx, uint64_t *row_off, uint32_t *nbrs);
+
 /* ---- SearchRoarGraph, whole batch -------------------------------------------------------------
  * queries: nq x dim (same padded dim as the base; normalised by the caller for COSINE).
  * Outputs (caller-allocated): ids[nq*k], dists[nq*k] = internal distances in (distance asc, id asc) order

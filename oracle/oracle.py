@@ -126,6 +126,8 @@ class Reference:
                                           C.c_uint, C.c_int]
         L.ref_index_load.restype = C.c_void_p
         L.ref_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_int]
+        L.ref_index_from_memory.restype = C.c_void_p
+        L.ref_index_from_memory.argtypes = [_f32p, C.c_uint64, C.c_uint, C.c_int, C.c_char_p, C.c_uint, C.c_int]
         L.ref_index_need_normalize.argtypes = [C.c_void_p]
         L.ref_normalize_rows.argtypes = [_f32p, C.c_uint64, C.c_uint]
         L.ref_search_roargraph.restype = C.c_int
@@ -160,6 +162,15 @@ class Reference:
     def index_load(self, base_fbin, index_file, metric, padded_dim, threads, quiet=True):
         h = self.lib.ref_index_load(base_fbin.encode(), index_file.encode(), METRIC[metric], padded_dim, threads,
                                     int(quiet))
+        if not h:
+            raise RuntimeError("reference index load failed: " + self.err())
+        return h
+
+    def index_from_memory(self, base, index_file, metric, threads, quiet=True):
+        """The reference index over a base array already in memory (padded x8, normalised for cosine); `base` must
+        outlive the handle."""
+        h = self.lib.ref_index_from_memory(base, base.shape[0], base.shape[1], METRIC[metric], index_file.encode(),
+                                           threads, int(quiet))
         if not h:
             raise RuntimeError("reference index load failed: " + self.err())
         return h

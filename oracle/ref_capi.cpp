@@ -48,6 +48,13 @@ struct RefIndex {
     unsigned dim;   // padded (x8) dimension the index was constructed with
     unsigned nd;
     int threads_inited;
+    bool own_base;
+};
+// data_bp_ is a protected member of efanna2e::Index (include/efanna2e/index.h:62): a derived class may point the
+// unmodified reference at a base array that is already in memory instead of re-reading an fbin file.
+struct MemIndex : efanna2e::IndexBipartite {
+    using efanna2e::IndexBipartite::IndexBipartite;
+    void set_base(const float *p) { data_bp_ = p; }
 };
 }  // namespace
 
@@ -114,6 +121,30 @@ void *ref_index_load(const char *base_fbin, const char *index_file, int metric, 
         r->dim = padded_dim;
         r->nd = base_num;
         r->threads_inited = (int)num_threads;
+        r->own_base = true;
+        return r;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+// Same as ref_index_load, but the base rows (padded to x8, already normalised for COSINE — what LoadVectorData
+// would have produced, src/index_bipartite.cpp:2679-2686) are handed over in memory; the caller keeps ownership.
+void *ref_index_from_memory(const float *base, uint64_t nd, unsigned padded_dim, int metric, const char *index_file,
+                            unsigned num_threads, int quiet) {
+    try {
+        Quiet q(quiet != 0);
+        auto *r = new RefIndex();
+        auto *mi = new MemIndex(padded_dim, nd, to_metric(metric), nullptr);
+        mi->set_base(base);
+        r->index = mi;
+        r->index->LoadProjectionGraph(index_file);
+        r->index->InitVisitedListPool(num_threads);
+        r->dim = padded_dim;
+        r->nd = (unsigned)nd;
+        r->threads_inited = (int)num_threads;
+        r->own_base = false;
         return r;
     } catch (const std::exception &e) {
         g_err = e.what();
@@ -181,7 +212,7 @@ void ref_index_free(void *h) {
     if (!r) return;
     // The reference never frees its base array or graph (IndexBipartite::~IndexBipartite is empty); release the
     // big base block ourselves so test processes do not accumulate it.
-    free((void *)r->index->GetBasePointSet());
+    if (r->own_base) free((void *)r->index->GetBasePointSet());
     delete r->index;
     delete r;
 }

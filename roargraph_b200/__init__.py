@@ -60,6 +60,9 @@ def lib() -> C.CDLL:
         L.rg_index_set_graph.argtypes = [vp, u32, vp, vp]
         L.rg_index_set_bipartite.argtypes = [vp, u64, vp, vp]
         L.rg_index_destroy.argtypes = [vp]
+        L.rg_index_build_roargraph.argtypes = [vp, vp, C.c_int, u64, u32, u32, u32, u32, u32]
+        L.rg_index_graph_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]
+        L.rg_index_get_graph.argtypes = [vp, vp, vp]
         L.rg_search_roargraph.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
         L.rg_search_roargraph_dev.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp]
         L.rg_index_check.argtypes = [vp, vp]
@@ -151,6 +154,32 @@ class RoarIndex:
         row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
         nbrs = np.ascontiguousarray(nbrs, dtype=np.uint32)
         _check(lib().rg_index_set_bipartite(self._h, row_off.shape[0] - 1, _np_ptr(row_off), _np_ptr(nbrs)))
+
+    def build_roargraph(self, knn_ids, M_sq: int = 100, M_pjbp: int = 35, L_pjpq: int = 500, n_rounds: int = 0) -> None:
+        """BuildRoarGraph on the device (src/index_bipartite.cpp:143-233) from the training queries' kNN id lists
+        (numpy uint32/int32 [nsq, K] or a CUDA int32 tensor); parameters as tests/test_build_roargraph.cpp:52-60."""
+        if isinstance(knn_ids, np.ndarray):
+            a = np.ascontiguousarray(knn_ids).view(np.uint32)
+            _check(lib().rg_index_build_roargraph(self._h, _np_ptr(a), 0, a.shape[0], a.shape[1], M_sq, M_pjbp, L_pjpq,
+                                                  n_rounds))
+        else:
+            if not knn_ids.is_cuda or not knn_ids.is_contiguous() or knn_ids.element_size() != 4:
+                raise RgError(RG_EINVAL, "knn_ids must be a contiguous 32-bit CUDA tensor")
+            _check(lib().rg_index_build_roargraph(self._h, C.c_void_p(knn_ids.data_ptr()), 1, knn_ids.shape[0],
+                                                  knn_ids.shape[1], M_sq, M_pjbp, L_pjpq, n_rounds))
+
+    def graph_size(self):
+        nnz, ep, md = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        _check(lib().rg_index_graph_size(self._h, C.byref(nnz), C.byref(ep), C.byref(md)))
+        return dict(nnz=nnz.value, ep=ep.value, max_degree=md.value)
+
+    def get_graph(self):
+        """-> (ep, row_off u64[nd+1], nbrs u32[nnz]): what SaveProjectionGraph writes (src/index_bipartite.cpp:2606-2619)."""
+        g = self.graph_size()
+        row_off = np.empty(self.nd + 1, dtype=np.uint64)
+        nbrs = np.empty(g["nnz"], dtype=np.uint32)
+        _check(lib().rg_index_get_graph(self._h, _np_ptr(row_off), _np_ptr(nbrs)))
+        return g["ep"], row_off, nbrs
 
     # -- SearchRoarGraph ---------------------------------------------------------------------------------------
     def search(self, queries: np.ndarray, k: int, L_pq: int):

@@ -1,0 +1,581 @@
+// rg_build.cu — BuildRoarGraph on sm_100a: a bulk-synchronous restatement of the reference's index construction
+// (IndexBipartite::BuildRoarGraph -> LinkProjection, src/index_bipartite.cpp:143-233, :1043-1277; paths relative to
+// /root/reference).  SURVEY.md 8(f)-1: the connectivity-enhancement search is the same beam-search kernel as the
+// query path (rg_search.cu, mode 2) and is 85-94 % of the reference's build time.
+//
+// The reference mutates the graph from 64 OpenMP threads under per-node mutexes, so its output depends on thread
+// timing; parity for this row is therefore statistical (degree distribution, recall at a given L_pq), not id-exact.
+// Here every phase is a deterministic data-parallel pass:
+//   1a  projection      per training query: pivot = its nearest base row; prune its remaining M_sq-1 neighbours
+//                       around the pivot (PruneBiSearchBaseGetBase :1612-1694); the last query of a pivot wins (:1093).
+//   1b  reverse edges   twice (ProjectionAddReverse inside the loop :1095 and over all nodes :1105-1108): every edge
+//                       u->v offers u to v; lists above M_pjbp are re-pruned (PruneProjectionReverseCandidates :1527-1610).
+//   3   connectivity    in rounds over contiguous node ranges: beam search of every base row on the supply graph at
+//                       L_pjpq (SearchProjectionGraphInternal :1279-1350), prune the expanded set
+//                       (PruneProjectionBaseSearchCandidates :1846-1940) -> supply[v]; reverse edges with cap 2*M_pjbp
+//                       re-pruned to M_pjbp (SupplyAddReverse :1352-1392, PruneProjectionInternalReverseCandidates :1434-1525).
+//   4   supply lists above M_pjbp re-pruned (:1224-1247); final row = projection ++ (supply \ projection) (:1251-1267).
+// One CTA per node does candidate assembly, distances to the node, a bitonic sort by (distance, id) and the greedy
+// occlusion scan with the selected rows staged in shared memory.
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "rg_internal.h"
+
+namespace rg {
+namespace {
+
+constexpr int kPruneThreads = 128;
+constexpr uint32_t kMaxCand = 1024;
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+struct PruneParams {
+    const float *base;
+    uint32_t dim, nd;
+    int l2;
+    int mode;  // 1 projection from kNN, 2 projection reverse, 3 supply from search, 4 supply reverse, 5 supply re-prune
+    uint32_t node_lo, n_nodes, M;
+    const uint32_t *knn;
+    uint32_t knn_stride, M_sq;
+    const int *owner;
+    uint32_t *proj, *supply;
+    uint32_t proj_stride, supply_stride;
+    const unsigned long long *in_keys;
+    const uint64_t *in_off;
+    const uint32_t *exp_ids;
+    const float *exp_dists;
+    const uint32_t *exp_cnt;
+    uint32_t exp_cap;
+};
+
+// warp-cooperative internal distance between two rows (a in shared or global memory, b in shared memory)
+__device__ __forceinline__ float warp_distance(const float *a, const float *b, uint32_t dim4, int l2, int lane) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(a);
+    const float4 *b4 = reinterpret_cast<const float4 *>(b);
+    float s = 0.f;
+    for (uint32_t i = lane; i < dim4; i += 32) {
+        const float4 x = a4[i], y = b4[i];
+        if (l2) {
+            const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+            s = fmaf(d0, d0, s);
+            s = fmaf(d1, d1, s);
+            s = fmaf(d2, d2, s);
+            s = fmaf(d3, d3, s);
+        } else {
+            s = fmaf(x.x, y.x, s);
+            s = fmaf(x.y, y.y, s);
+            s = fmaf(x.z, y.z, s);
+            s = fmaf(x.w, y.w, s);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    return l2 ? s : -s;
+}
+
+__device__ __forceinline__ bool list_has(const uint32_t *list, uint32_t n, uint32_t id) {
+    for (uint32_t i = 0; i < n; ++i)
+        if (list[i] == id) return true;
+    return false;
+}
+
+// Shared-memory layout (dynamic): keys[kMaxCand] u64 | raw ids[kMaxCand] | own[128] | skip[128] | result[128] |
+// vrow[dim] | prow[dim] | sel[M * dim]
+__global__ void __launch_bounds__(kPruneThreads) prune_kernel(const PruneParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
+    uint32_t *raw = reinterpret_cast<uint32_t *>(keys + kMaxCand);
+    uint32_t *own = raw + kMaxCand;
+    uint32_t *skip = own + 128;
+    uint32_t *result = skip + 128;
+    float *vrow = reinterpret_cast<float *>(result + 128);
+    float *prow = vrow + p.dim;
+    float *sel = prow + p.dim;
+    __shared__ uint32_t s_cnt, s_warp_tot[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t v = p.node_lo + blockIdx.x;
+    const uint32_t dim4 = p.dim >> 2;
+    const uint32_t M = p.M;
+
+    uint32_t n = 0;        // candidates in raw[]
+    uint32_t n_skip = 0;   // skip list (first pick must not already be a projection neighbour, :1859-1862)
+    bool have_dists = false, fill = false;
+    uint32_t *target = nullptr;
+    uint32_t target_cap = 0;
+
+    if (p.mode == 1) {
+        const int o = p.owner[v];
+        if (o < 0) return;
+        n = min(p.M_sq, kMaxCand);
+        for (uint32_t i = tid; i < n; i += kPruneThreads) raw[i] = p.knn[(size_t)o * p.knn_stride + i];
+        fill = true;
+        target = p.proj + (size_t)v * p.proj_stride;
+        target_cap = M;
+    } else if (p.mode == 3) {
+        const uint32_t i0 = blockIdx.x;
+        n = min(p.exp_cnt[i0], min(p.exp_cap, kMaxCand));
+        for (uint32_t i = tid; i < n; i += kPruneThreads) {
+            const uint32_t id = p.exp_ids[(size_t)i0 * p.exp_cap + i];
+            raw[i] = id;
+            keys[i] = ((unsigned long long)f2ord(p.exp_dists[(size_t)i0 * p.exp_cap + i]) << 32) | id;
+        }
+        have_dists = true;
+        const uint32_t *prow_ = p.proj + (size_t)v * p.proj_stride;
+        n_skip = min(prow_[0], 128u);
+        for (uint32_t i = tid; i < n_skip; i += kPruneThreads) skip[i] = prow_[1 + i];
+        target = p.supply + (size_t)v * p.supply_stride;
+        target_cap = M;
+    } else {
+        // modes 2, 4, 5: own list (+ incoming reverse offers)
+        uint32_t *grow = (p.mode == 2) ? p.proj + (size_t)v * p.proj_stride : p.supply + (size_t)v * p.supply_stride;
+        const uint32_t keep_cap = (p.mode == 2) ? M : 2 * M;  // :1360 SupplyAddReverse works with M_pjbp * 2
+        const uint32_t n_own = min(grow[0], 128u);
+        uint64_t ib = 0, ie = 0;
+        if (p.mode != 5) {
+            ib = p.in_off[v];
+            ie = p.in_off[v + 1];
+            if (ib == ie) return;
+        } else {
+            if (n_own <= M) return;
+            const uint32_t *prow_ = p.proj + (size_t)v * p.proj_stride;
+            n_skip = min(prow_[0], 128u);
+            for (uint32_t i = tid; i < n_skip; i += kPruneThreads) skip[i] = prow_[1 + i];
+        }
+        for (uint32_t i = tid; i < n_own; i += kPruneThreads) {
+            own[i] = grow[1 + i];
+            raw[i] = own[i];
+        }
+        if (tid == 0) s_cnt = n_own;
+        __syncthreads();
+        // ordered compaction of the offers that are new to this list
+        for (uint64_t c0 = ib; c0 < ie; c0 += kPruneThreads) {
+            const uint64_t j = c0 + tid;
+            uint32_t src = 0;
+            bool isnew = false;
+            if (j < ie) {
+                src = (uint32_t)p.in_keys[j];
+                isnew = src != v && !list_has(own, n_own, src);
+            }
+            const uint32_t bal = __ballot_sync(kFullMask, isnew);
+            if (lane == 0) s_warp_tot[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t off = s_cnt;
+            for (int w2 = 0; w2 < warp; ++w2) off += s_warp_tot[w2];
+            off += __popc(bal & ((1u << lane) - 1u));
+            if (isnew && off < kMaxCand) raw[off] = src;
+            __syncthreads();
+            if (tid == 0) s_cnt = min(s_cnt + s_warp_tot[0] + s_warp_tot[1] + s_warp_tot[2] + s_warp_tot[3], kMaxCand);
+            __syncthreads();
+            if (s_cnt >= kMaxCand) break;
+        }
+        n = s_cnt;
+        if (p.mode != 5) {
+            if (n == n_own) return;  // nothing new
+            if (n <= keep_cap) {     // room left: plain append (:1364-1366 / :1401-1403)
+                for (uint32_t i = n_own + tid; i < n; i += kPruneThreads) grow[1 + i] = raw[i];
+                __syncthreads();
+                if (tid == 0) grow[0] = n;
+                return;
+            }
+        }
+        fill = (p.mode == 2);  // PruneProjectionReverseCandidates pads back to M_pjbp (:1603-1607); the supply variants do not
+        target = grow;
+        target_cap = M;
+    }
+    __syncthreads();
+
+    // the node's own row
+    for (uint32_t i = tid; i < dim4; i += kPruneThreads)
+        reinterpret_cast<float4 *>(vrow)[i] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)v * p.dim) + i);
+    __syncthreads();
+    if (!have_dists) {
+        for (uint32_t c = warp; c < n; c += kPruneThreads / 32) {
+            const uint32_t id = raw[c];
+            if (id >= p.nd) {  // not a base row (e.g. a -1 filler in a short kNN list)
+                if (lane == 0) keys[c] = ~0ull;
+                continue;
+            }
+            const float d = warp_distance(p.base + (size_t)id * p.dim, vrow, dim4, p.l2, lane);
+            if (lane == 0) keys[c] = ((unsigned long long)f2ord(d) << 32) | id;
+        }
+    }
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    for (uint32_t i = n + tid; i < m; i += kPruneThreads) keys[i] = ~0ull;
+    __syncthreads();
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (m >> 1); i += kPruneThreads) {
+                const uint32_t lo = 2 * i - (i & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // greedy occlusion scan over the sorted candidates (:1871-1890 and its siblings)
+    uint32_t nres = 0;
+    uint32_t prev = 0xffffffffu;
+    for (uint32_t i = 0; i < n && nres < target_cap; ++i) {
+        const unsigned long long key = keys[i];
+        const uint32_t id = (uint32_t)key;
+        if (id == v || id == prev || id >= p.nd) continue;
+        prev = id;
+        if (nres == 0 && n_skip && list_has(skip, n_skip, id)) continue;
+        const float pd = ord2f((uint32_t)(key >> 32));
+        for (uint32_t j = tid; j < dim4; j += kPruneThreads)
+            reinterpret_cast<float4 *>(prow)[j] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)id * p.dim) + j);
+        __syncthreads();
+        int occ = 0;
+        for (uint32_t r = warp; r < nres; r += kPruneThreads / 32) {
+            const float djk = warp_distance(prow, sel + (size_t)r * p.dim, dim4, p.l2, lane);
+            if (djk < pd) {
+                occ = 1;
+                break;
+            }
+        }
+        occ = __syncthreads_or(occ);
+        if (!occ) {
+            for (uint32_t j = tid; j < dim4; j += kPruneThreads)
+                reinterpret_cast<float4 *>(sel + (size_t)nres * p.dim)[j] = reinterpret_cast<const float4 *>(prow)[j];
+            if (tid == 0) result[nres] = id;
+            ++nres;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (fill) {  // pad with the nearest remaining candidates (:1680-1688, :1603-1607)
+            uint32_t pv = 0xffffffffu;
+            for (uint32_t i = 0; i < n && nres < target_cap; ++i) {
+                const uint32_t id = (uint32_t)keys[i];
+                if (id == v || id == pv || id >= p.nd) continue;
+                pv = id;
+                if (!list_has(result, nres, id)) result[nres++] = id;
+            }
+        }
+        target[0] = nres;
+        for (uint32_t i = 0; i < nres; ++i) target[1 + i] = result[i];
+    }
+}
+
+__global__ void owner_kernel(const uint32_t *knn, uint32_t knn_stride, uint64_t nsq, uint32_t nd, int *owner) {
+    const uint64_t sq = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sq >= nsq) return;
+    const uint32_t piv = knn[sq * knn_stride];
+    if (piv < nd) atomicMax(owner + piv, (int)sq);  // "projection_graph_[cur_tgt] = pruned_list": the last writer wins
+}
+
+// keys (dst << 32 | src) for every edge of nodes [lo, lo + n); unused slots = ~0
+__global__ void emit_edges_kernel(const uint32_t *adj, uint32_t stride, uint32_t lo, uint32_t n, uint32_t slots,
+                                  unsigned long long *keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)n * slots) return;
+    const uint32_t u = lo + (uint32_t)(i / slots), j = (uint32_t)(i % slots);
+    const uint32_t *row = adj + (size_t)u * stride;
+    keys[i] = (j < row[0]) ? (((unsigned long long)row[1 + j] << 32) | u) : ~0ull;
+}
+
+__global__ void seg_offsets_kernel(const unsigned long long *keys, uint64_t n, uint32_t nd, uint64_t *off) {
+    const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > nd) return;
+    const unsigned long long want = (unsigned long long)d << 32;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    off[d] = lo;
+}
+
+// CalculateProjectionep (:2004-2041): centroid, then the row closest to it in squared L2 (lowest id on ties)
+__global__ void colsum_kernel(const float *base, uint64_t nd, uint32_t dim, double *sum) {
+    const uint32_t d = threadIdx.x;
+    const uint64_t rows_per = (nd + gridDim.x - 1) / gridDim.x;
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per, r1 = min(nd, r0 + rows_per);
+    for (uint32_t dd = d; dd < dim; dd += blockDim.x) {
+        double s = 0.0;
+        for (uint64_t r = r0; r < r1; ++r) s += (double)base[r * dim + dd];
+        atomicAdd(sum + dd, s);
+    }
+}
+__global__ void closest_to_center_kernel(const float *base, uint64_t nd, uint32_t dim, const double *sum,
+                                         unsigned long long *best) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nd) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (uint32_t j = lane; j < dim; j += 32) {
+        const float c = (float)(sum[j] / (double)nd);
+        const float df = c - base[row * dim + j];
+        s = fmaf(df, df, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    if (lane == 0) atomicMin(best, ((unsigned long long)f2ord(s) << 32) | (uint32_t)row);
+}
+
+__global__ void copy_rows_kernel(const uint32_t *src, uint32_t sstride, uint32_t *dst, uint32_t dstride, uint64_t nd) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd * sstride) return;
+    const uint64_t u = i / sstride;
+    const uint32_t j = (uint32_t)(i % sstride);
+    dst[u * dstride + j] = src[i];
+}
+
+// final row = projection ++ (supply \ projection), at most 2*M supply entries (:1251-1267)
+__global__ void merge_rows_kernel(const uint32_t *proj, uint32_t pstride, const uint32_t *supply, uint32_t sstride,
+                                  uint32_t *out, uint32_t ostride, uint64_t nd, uint32_t M, uint32_t *max_deg) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nd) return;
+    const uint32_t *pr = proj + u * pstride, *sr = supply + u * sstride;
+    uint32_t *o = out + u * ostride;
+    uint32_t n = 0;
+    const uint32_t np = pr[0];
+    for (uint32_t i = 0; i < np; ++i) o[1 + n++] = pr[1 + i];
+    uint32_t added = 0;
+    for (uint32_t j = 0; j < sr[0] && added < 2 * M && n + 1 < ostride; ++j) {
+        const uint32_t id = sr[1 + j];
+        bool dup = false;
+        for (uint32_t i = 0; i < n; ++i)
+            if (o[1 + i] == id) { dup = true; break; }
+        if (!dup) {
+            o[1 + n++] = id;
+            ++added;
+        }
+    }
+    o[0] = n;
+    for (uint32_t i = n + 1; i < ostride; ++i) o[i] = 0xffffffffu;
+    atomicMax(max_deg, n);
+}
+
+struct Buf {
+    void *p = nullptr;
+    ~Buf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { RG_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); return RG_OK; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+size_t prune_smem(uint32_t dim, uint32_t M) {
+    return kMaxCand * 8 + kMaxCand * 4 + 3 * 128 * 4 + (size_t)(2 + M) * dim * 4;
+}
+
+}  // namespace
+
+// Sorted reverse-edge offers for the edges of nodes [lo, lo + n) of `adj`: keys (dst << 32 | src) ascending + per-dst offsets.
+static int gather_offers(const uint32_t *adj, uint32_t stride, uint32_t lo, uint32_t n, uint32_t slots, uint32_t nd,
+                         unsigned long long *keys_a, unsigned long long *keys_b, void *cub_tmp, size_t cub_bytes,
+                         uint64_t *in_off, const unsigned long long **sorted, cudaStream_t s) {
+    const uint64_t total = (uint64_t)n * slots;
+    emit_edges_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(adj, stride, lo, n, slots, keys_a);
+    int end_bit = 33;
+    while (end_bit < 64 && (1ull << (end_bit - 32)) <= nd) ++end_bit;
+    (void)end_bit;  // padding keys are all-ones: sort on the full 64 bits so they stay at the end
+    RG_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, total, 0, 64, s));
+    seg_offsets_kernel<<<(nd + 1 + 255) / 256, 256, 0, s>>>(keys_b, total, nd, in_off);
+    *sorted = keys_b;
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+__global__ void degree_sum_kernel(const uint32_t *adj, uint32_t stride, uint64_t nd, unsigned long long *total) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long d = u < nd ? adj[u * stride] : 0ull;
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31) == 0 && d) atomicAdd(total, d);
+}
+
+int adjacency_nnz_device(const uint32_t *d_adj, uint32_t stride, uint64_t nd, uint64_t *nnz) {
+    unsigned long long *d_total = nullptr, h = 0;
+    RG_CUDA(cudaMalloc(&d_total, 8));
+    cudaMemset(d_total, 0, 8);
+    degree_sum_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(d_adj, stride, nd, d_total);
+    cudaError_t e = cudaMemcpy(&h, d_total, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_total);
+    if (e != cudaSuccess) return cuda_fail(e, "adjacency_nnz");
+    *nnz = h;
+    return RG_OK;
+}
+
+int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, uint32_t knn_stride, uint32_t M_sq,
+                           uint32_t M, uint32_t L, uint32_t n_rounds, cudaStream_t s) {
+    const uint32_t nd = (uint32_t)idx->nd;
+    const uint32_t dim = idx->dim;
+    const int l2 = idx->metric == RG_METRIC_L2 ? 1 : 0;
+    if (M == 0 || M > 64) { set_error("rg_index_build_roargraph: M_pjbp must be in [1, 64]"); return RG_EINVAL; }
+    if (M_sq == 0 || M_sq > knn_stride) { set_error("rg_index_build_roargraph: M_sq exceeds the kNN list length"); return RG_EINVAL; }
+    if (L == 0 || L >= (1u << 20)) { set_error("rg_index_build_roargraph: bad L_pjpq"); return RG_EINVAL; }
+    const uint32_t pstride = (M + 1 + 7) & ~7u, sstride = (2 * M + 1 + 7) & ~7u, ostride = sstride;
+    const size_t smem = prune_smem(dim, M);
+    if (smem > 227u * 1024u) { set_error("rg_index_build_roargraph: dim * M_pjbp too large for the prune kernel"); return RG_EINVAL; }
+    RG_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    // rounds of the connectivity phase
+    uint32_t batch;
+    if (n_rounds == 0) {
+        batch = std::max<uint32_t>(256u, std::min<uint32_t>(1u << 19, (nd + 47) / 48));
+    } else {
+        batch = (nd + n_rounds - 1) / n_rounds;
+    }
+    batch = std::min(batch, nd);
+    const uint32_t exp_cap = std::min<uint32_t>(kMaxCand, L + 64);
+
+    Buf b_proj, b_supply, b_owner, b_keys_a, b_keys_b, b_cub, b_off, b_sum, b_best, b_exp_ids, b_exp_d, b_exp_cnt, b_out, b_maxdeg;
+    int rc;
+    const uint64_t offer_slots = std::max<uint64_t>((uint64_t)nd * M, (uint64_t)batch * 2 * M);
+    size_t cub_bytes = 0;
+    RG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                           offer_slots, 0, 64, s));
+    if ((rc = b_proj.alloc((size_t)nd * pstride * 4)) || (rc = b_supply.alloc((size_t)nd * sstride * 4)) ||
+        (rc = b_owner.alloc((size_t)nd * 4)) || (rc = b_keys_a.alloc(offer_slots * 8)) ||
+        (rc = b_keys_b.alloc(offer_slots * 8)) || (rc = b_cub.alloc(cub_bytes)) || (rc = b_off.alloc(((size_t)nd + 1) * 8)) ||
+        (rc = b_sum.alloc(dim * 8)) || (rc = b_best.alloc(8)) || (rc = b_exp_ids.alloc((size_t)batch * exp_cap * 4)) ||
+        (rc = b_exp_d.alloc((size_t)batch * exp_cap * 4)) || (rc = b_exp_cnt.alloc((size_t)batch * 4)) ||
+        (rc = b_maxdeg.alloc(4)))
+        return rc;
+    uint32_t *proj = b_proj.as<uint32_t>(), *supply = b_supply.as<uint32_t>();
+    RG_CUDA(cudaMemsetAsync(proj, 0, (size_t)nd * pstride * 4, s));
+    RG_CUDA(cudaMemsetAsync(supply, 0, (size_t)nd * sstride * 4, s));
+
+    // entry point
+    RG_CUDA(cudaMemsetAsync(b_sum.p, 0, dim * 8, s));
+    RG_CUDA(cudaMemsetAsync(b_best.p, 0xff, 8, s));
+    colsum_kernel<<<std::min<uint32_t>(nd, 4096), 256, 0, s>>>(idx->d_base, nd, dim, b_sum.as<double>());
+    closest_to_center_kernel<<<(nd + 7) / 8, 256, 0, s>>>(idx->d_base, nd, dim, b_sum.as<double>(), b_best.as<unsigned long long>());
+    unsigned long long h_best = 0;
+    RG_CUDA(cudaMemcpyAsync(&h_best, b_best.p, 8, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    const uint32_t ep = (uint32_t)h_best;
+
+    PruneParams pp{};
+    pp.base = idx->d_base;
+    pp.dim = dim;
+    pp.nd = nd;
+    pp.l2 = l2;
+    pp.M = M;
+    pp.knn = d_knn;
+    pp.knn_stride = knn_stride;
+    pp.M_sq = M_sq;
+    pp.owner = b_owner.as<int>();
+    pp.proj = proj;
+    pp.supply = supply;
+    pp.proj_stride = pstride;
+    pp.supply_stride = sstride;
+    pp.in_off = b_off.as<uint64_t>();
+
+    // phase 1a
+    RG_CUDA(cudaMemsetAsync(b_owner.p, 0xff, (size_t)nd * 4, s));
+    owner_kernel<<<(unsigned)((nsq + 255) / 256), 256, 0, s>>>(d_knn, knn_stride, nsq, nd, b_owner.as<int>());
+    pp.mode = 1;
+    pp.node_lo = 0;
+    pp.n_nodes = nd;
+    prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
+    RG_CUDA(cudaGetLastError());
+    // phase 1b, twice
+    for (int round = 0; round < 2; ++round) {
+        const unsigned long long *sorted = nullptr;
+        rc = gather_offers(proj, pstride, 0, nd, M, nd, b_keys_a.as<unsigned long long>(), b_keys_b.as<unsigned long long>(),
+                           b_cub.p, cub_bytes, b_off.as<uint64_t>(), &sorted, s);
+        if (rc != RG_OK) return rc;
+        pp.mode = 2;
+        pp.in_keys = sorted;
+        prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
+        RG_CUDA(cudaGetLastError());
+    }
+    // supply graph starts as the projection graph (:1179-1184)
+    copy_rows_kernel<<<(unsigned)(((uint64_t)nd * pstride + 255) / 256), 256, 0, s>>>(proj, pstride, supply, sstride, nd);
+
+    // phase 3
+    SearchParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.base = idx->d_base;
+    sp.nd = nd;
+    sp.dim = dim;
+    sp.k = 1;
+    sp.L = L;
+    sp.metric_l2 = l2;
+    sp.tag_stride = idx->tag_stride;
+    sp.counter = idx->d_counter;
+    sp.stats = idx->d_stats;
+    sp.adj = supply;
+    sp.adj_stride = sstride;
+    sp.ep = ep;
+    sp.n_init = 1;
+    sp.exp_ids = b_exp_ids.as<uint32_t>();
+    sp.exp_dists = b_exp_d.as<float>();
+    sp.exp_cnt = b_exp_cnt.as<uint32_t>();
+    sp.exp_cap = exp_cap;
+    pp.exp_ids = sp.exp_ids;
+    pp.exp_dists = sp.exp_dists;
+    pp.exp_cnt = sp.exp_cnt;
+    pp.exp_cap = exp_cap;
+    for (uint32_t lo = 0; lo < nd; lo += batch) {
+        const uint32_t n = std::min(batch, nd - lo);
+        sp.nq = n;
+        sp.node_lo = lo;
+        SearchLaunch l;
+        rc = plan_search(sp, l, sm_count(), std::max(idx->n_slots, affordable_slots(idx)));
+        if (rc != RG_OK) return rc;
+        rc = ensure_tags(idx, l.grid * l.warps_per_cta);
+        if (rc != RG_OK) return rc;
+        sp.tags = idx->d_tags;
+        sp.slot_epoch = idx->d_slot_epoch;
+        rc = launch_build_search(sp, l, s);
+        if (rc != RG_OK) return rc;
+        pp.mode = 3;
+        pp.node_lo = lo;
+        pp.n_nodes = n;
+        prune_kernel<<<n, kPruneThreads, smem, s>>>(pp);
+        RG_CUDA(cudaGetLastError());
+        const unsigned long long *sorted = nullptr;
+        rc = gather_offers(supply, sstride, lo, n, 2 * M, nd, b_keys_a.as<unsigned long long>(), b_keys_b.as<unsigned long long>(),
+                           b_cub.p, cub_bytes, b_off.as<uint64_t>(), &sorted, s);
+        if (rc != RG_OK) return rc;
+        pp.mode = 4;
+        pp.node_lo = 0;
+        pp.n_nodes = nd;
+        pp.in_keys = sorted;
+        prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
+        RG_CUDA(cudaGetLastError());
+    }
+    // phase 4
+    pp.mode = 5;
+    pp.node_lo = 0;
+    pp.n_nodes = nd;
+    prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
+    RG_CUDA(cudaGetLastError());
+    if ((rc = b_out.alloc((size_t)nd * ostride * 4))) return rc;
+    RG_CUDA(cudaMemsetAsync(b_maxdeg.p, 0, 4, s));
+    merge_rows_kernel<<<(nd + 255) / 256, 256, 0, s>>>(proj, pstride, supply, sstride, b_out.as<uint32_t>(), ostride, nd, M,
+                                                        b_maxdeg.as<uint32_t>());
+    RG_CUDA(cudaGetLastError());
+    uint32_t h_max = 0;
+    RG_CUDA(cudaMemcpyAsync(&h_max, b_maxdeg.p, 4, cudaMemcpyDeviceToHost, s));
+    RG_CUDA(cudaStreamSynchronize(s));
+    if (idx->d_adj) cudaFree(idx->d_adj);
+    idx->d_adj = b_out.as<uint32_t>();
+    b_out.p = nullptr;  // ownership moves to the index
+    idx->adj_stride = ostride;
+    idx->max_deg = h_max;
+    idx->ep = ep;
+    idx->has_graph = true;
+    return RG_OK;
+}
+
+}  // namespace rg

@@ -41,60 +41,16 @@ static int ensure_device() {
     return RG_OK;
 }
 
-template <class T>
-struct DevBuf {  // grow-only device scratch
-    T *p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t n) {
-        if (n <= cap) return RG_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        RG_CUDA(cudaMalloc(&p, n * sizeof(T)));
-        cap = n;
-        return RG_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
 }  // namespace rg
 
 using namespace rg;
 
-struct rg_index {
-    uint64_t nd = 0;
-    uint32_t dim = 0;
-    int metric = 0;
-    const float *d_base = nullptr;
-    bool own_base = false;
-    // projection graph, fixed-stride rows [deg, ids...]
-    uint32_t *d_adj = nullptr;
-    uint32_t adj_stride = 0, ep = 0, max_deg = 0;
-    bool has_graph = false;
-    // bipartite graph, CSR
-    uint64_t *d_row_off = nullptr;
-    uint32_t *d_csr = nullptr;
-    uint64_t n_total = 0;
-    bool has_bipartite = false;
-    // visited tags
-    uint8_t *d_tags = nullptr;
-    uint32_t *d_slot_epoch = nullptr;
-    uint32_t n_slots = 0;
-    uint64_t tag_stride = 0;
-    // per-call scratch
-    uint32_t *d_counter = nullptr;
-    unsigned long long *d_stats = nullptr;
-    DevBuf<float> q, dists;
-    DevBuf<uint32_t> ids, cmps, hops, init;
-    SearchLaunch last_launch{};
-    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
-};
+namespace rg {
+int sm_count() { return g_sm_count; }
+int ensure_device_ready() { return ensure_device(); }
+}
 
-static int ensure_tags(rg_index *idx, uint32_t slots) {
+int rg::ensure_tags(rg_index *idx, uint32_t slots) {
     if (slots <= idx->n_slots) return RG_OK;
     if (idx->d_tags) cudaFree(idx->d_tags);
     if (idx->d_slot_epoch) cudaFree(idx->d_slot_epoch);
@@ -111,7 +67,7 @@ static int ensure_tags(rg_index *idx, uint32_t slots) {
 }
 
 // Number of query slots (resident warps) whose tag arrays fit in a bounded share of free HBM.
-static uint32_t affordable_slots(rg_index *idx) {
+uint32_t rg::affordable_slots(rg_index *idx) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 64;
     size_t budget = (free_b + (size_t)idx->n_slots * idx->tag_stride) / 3;  // at most a third of what is free
@@ -297,6 +253,56 @@ int rg_index_destroy(rg_index *idx) {
     idx->init.release();
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
+    return RG_OK;
+}
+
+int rg_index_build_roargraph(rg_index *idx, const uint32_t *knn_ids, int knn_on_device, uint64_t nsq,
+                             uint32_t knn_stride, uint32_t M_sq, uint32_t M_pjbp, uint32_t L_pjpq, uint32_t n_rounds) {
+    if (!idx || !knn_ids || nsq == 0 || knn_stride == 0) { set_error("rg_index_build_roargraph: null/empty argument"); return RG_EINVAL; }
+    const uint32_t *d_knn = knn_ids;
+    uint32_t *tmp = nullptr;
+    if (!knn_on_device) {
+        RG_CUDA(cudaMalloc(&tmp, nsq * knn_stride * sizeof(uint32_t)));
+        cudaError_t e = cudaMemcpy(tmp, knn_ids, nsq * knn_stride * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "kNN upload"); }
+        d_knn = tmp;
+    }
+    int rc = build_roargraph_device(idx, d_knn, nsq, knn_stride, M_sq, M_pjbp, L_pjpq, n_rounds, idx->stream);
+    if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+int rg_index_graph_size(rg_index *idx, uint64_t *nnz, uint32_t *ep, uint32_t *max_degree) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    if (!idx->has_graph) { set_error("projection graph not set"); return RG_ESTATE; }
+    uint64_t total = 0;
+    int rc = adjacency_nnz_device(idx->d_adj, idx->adj_stride, idx->nd, &total);
+    if (rc != RG_OK) return rc;
+    if (nnz) *nnz = total;
+    if (ep) *ep = idx->ep;
+    if (max_degree) *max_degree = idx->max_deg;
+    return RG_OK;
+}
+
+int rg_index_get_graph(rg_index *idx, uint64_t *row_off, uint32_t *nbrs) {
+    if (!idx || !row_off) { set_error("rg_index_get_graph: null argument"); return RG_EINVAL; }
+    if (!idx->has_graph) { set_error("projection graph not set"); return RG_ESTATE; }
+    const uint64_t nd = idx->nd;
+    const uint32_t stride = idx->adj_stride;
+    // stream the fixed-stride rows back in slabs and compact them into CSR
+    const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / (stride * 4ull));
+    std::vector<uint32_t> host(slab * stride);
+    row_off[0] = 0;
+    for (uint64_t u0 = 0; u0 < nd; u0 += slab) {
+        const uint64_t n = std::min(slab, nd - u0);
+        RG_CUDA(cudaMemcpy(host.data(), idx->d_adj + u0 * stride, n * stride * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t *row = host.data() + i * stride;
+            const uint64_t b = row_off[u0 + i];
+            if (nbrs) memcpy(nbrs + b, row + 1, (size_t)row[0] * 4);
+            row_off[u0 + i + 1] = b + row[0];
+        }
+    }
     return RG_OK;
 }
 

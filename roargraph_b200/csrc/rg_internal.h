@@ -36,6 +36,10 @@ struct SearchParams {
     float *out_dists;         // nq x k
     uint32_t *out_cmps;       // nq or null
     uint32_t *out_hops;       // nq or null
+    uint32_t *exp_ids;        // build mode: nq x exp_cap expanded node ids in expansion order
+    float *exp_dists;         //             and their distances to the query node
+    uint32_t *exp_cnt;        //             number recorded per query (<= exp_cap)
+    uint32_t exp_cap, node_lo; // build mode: query i is base row node_lo + i
     unsigned long long *stats; // [0]=cmps [1]=hops [2]=adj_words [3]=first error word
     uint32_t *counter;        // work-queue ticket
     uint64_t tag_stride;      // bytes per slot (>= nd, 16-aligned)
@@ -56,7 +60,71 @@ struct SearchLaunch {
 int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slots);
 int launch_roargraph(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
 int launch_bipartite(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
+int launch_build_search(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
 uint32_t max_search_slots(int sm_count);
+
+template <class T>
+struct DevBuf {  // grow-only device scratch
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return RG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        RG_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+        return RG_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace rg
+
+struct rg_index {
+    uint64_t nd = 0;
+    uint32_t dim = 0;
+    int metric = 0;
+    const float *d_base = nullptr;
+    bool own_base = false;
+    // projection graph, fixed-stride rows [deg, ids...]
+    uint32_t *d_adj = nullptr;
+    uint32_t adj_stride = 0, ep = 0, max_deg = 0;
+    bool has_graph = false;
+    // bipartite graph, CSR
+    uint64_t *d_row_off = nullptr;
+    uint32_t *d_csr = nullptr;
+    uint64_t n_total = 0;
+    bool has_bipartite = false;
+    // visited tags
+    uint8_t *d_tags = nullptr;
+    uint32_t *d_slot_epoch = nullptr;
+    uint32_t n_slots = 0;
+    uint64_t tag_stride = 0;
+    // per-call scratch
+    uint32_t *d_counter = nullptr;
+    unsigned long long *d_stats = nullptr;
+    rg::DevBuf<float> q, dists;
+    rg::DevBuf<uint32_t> ids, cmps, hops, init;
+    rg::SearchLaunch last_launch{};
+    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+};
+
+namespace rg {
+
+int sm_count();
+int ensure_device_ready();
+int ensure_tags(rg_index *idx, uint32_t slots);
+uint32_t affordable_slots(rg_index *idx);
+
+// BuildRoarGraph (rg_build.cu)
+int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, uint32_t knn_stride, uint32_t M_sq,
+                           uint32_t M, uint32_t L, uint32_t n_rounds, cudaStream_t s);
+int adjacency_nnz_device(const uint32_t *d_adj, uint32_t stride, uint64_t nd, uint64_t *nnz);
 
 // exact kNN (rg_knn.cu)
 int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,

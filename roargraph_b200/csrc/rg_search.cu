@@ -196,8 +196,9 @@ __device__ __forceinline__ bool queue_insert(WarpCtx &w, uint32_t L, float cd, u
 }
 
 // NeighborPriorityQueue::closest_unexpanded (neighbor.h:185-192): flag entry `cur`, advance to the next unflagged one.
-__device__ __forceinline__ uint32_t queue_pop(WarpCtx &w) {
+__device__ __forceinline__ uint32_t queue_pop(WarpCtx &w, float *dist_out = nullptr) {
     const uint32_t u = w.qi[w.cur] & kIdMask;
+    if (dist_out) *dist_out = w.qd[w.cur];
     __syncwarp();
     if (w.lane == 0) w.qi[w.cur] = u | kExpandedBit;
     __syncwarp();
@@ -266,7 +267,7 @@ __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchPara
 // Visited filter (visited_list_pool.h / src/index_bipartite.cpp:2378-2386): appends the not-yet-visited ids of
 // list[0..cnt) to cand[ncand..] and tags them.  Up to kCandCap ids per call; lists are duplicate-free (deduplicated at upload).
 __device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, uint8_t epoch, const uint32_t *list,
-                                                     uint32_t cnt, uint32_t ncand) {
+                                                     uint32_t cnt, uint32_t ncand, uint32_t exclude = 0xffffffffu) {
     const int lane = w.lane;
     uint32_t id[3];
     uint8_t tg[3];
@@ -281,7 +282,7 @@ __device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, 
     for (int j = 0; j < 3; ++j) tg[j] = valid[j] ? __ldcg(tags + id[j]) : epoch;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const bool fresh = valid[j] && tg[j] != epoch;
+        const bool fresh = valid[j] && tg[j] != epoch && id[j] != exclude;
         if (fresh) __stcg(tags + id[j], epoch);
         const uint32_t m = __ballot_sync(kFull, fresh);
         if (fresh) w.cand[ncand + __popc(m & ((1u << lane) - 1u))] = id[j];
@@ -298,8 +299,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-template <bool kL2, bool kBipartite>
+// kMode: 0 = SearchRoarGraph, 1 = SearchBipartiteGraph, 2 = SearchProjectionGraphInternal (the build's
+// connectivity-enhancement search, src/index_bipartite.cpp:1279-1350: the query is base row node_lo + ticket, that node
+// is never evaluated, the entry point IS marked visited, and the expanded nodes are the output).
+template <bool kL2, int kMode>
 __global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams p) {
+    constexpr bool kBipartite = kMode == 1;
+    constexpr bool kBuild = kMode == 2;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -342,7 +348,8 @@ __global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams 
             __threadfence_block();
         }
         {
-            const float4 *src = reinterpret_cast<const float4 *>(p.queries + (size_t)qidx * p.dim);
+            const float4 *src = reinterpret_cast<const float4 *>(
+                kBuild ? p.base + (size_t)(p.node_lo + qidx) * p.dim : p.queries + (size_t)qidx * p.dim);
             float4 *dst = reinterpret_cast<float4 *>(w.q);
             for (uint32_t i = lane; i < (p.dim >> 2); i += 32) dst[i] = __ldg(src + i);
         }
@@ -353,7 +360,10 @@ __global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams 
         uint32_t cmps = 0, hops = 0, adjw = 0;
         // entry points (:2323-2353 / :287-310)
         if (!kBipartite) {
-            if (lane == 0) w.cand[0] = p.ep;  // evaluated + inserted, NOT marked visited (:2349 is commented out)
+            if (lane == 0) {
+                w.cand[0] = p.ep;  // evaluated + inserted, NOT marked visited (:2349 is commented out)
+                if (kBuild) __stcg(tags + p.ep, (uint8_t)epoch);  // :1307 the build's search does mark it
+            }
             __syncwarp();
             evaluate_candidates<kL2>(w, p, 1, false);
         } else {
@@ -369,14 +379,20 @@ __global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams 
         }
 
         while (w.cur < w.size) {  // has_unexpanded_node
-            const uint32_t u = queue_pop(w);
+            float ud;
+            const uint32_t u = queue_pop(w, kBuild ? &ud : nullptr);
+            if (kBuild && lane == 0 && hops < p.exp_cap) {  // full_retset.push_back(cur_check_node) :1316
+                p.exp_ids[(size_t)qidx * p.exp_cap + hops] = u;
+                p.exp_dists[(size_t)qidx * p.exp_cap + hops] = ud;
+            }
             ++hops;
             if (!kBipartite) {
                 const uint32_t *arow = p.adj + (size_t)u * p.adj_stride;
                 const uint32_t deg = __ldg(arow);
                 adjw += deg;
                 for (uint32_t off = 0; off < deg; off += kCandCap) {
-                    const uint32_t n = filter_unvisited(w, tags, (uint8_t)epoch, arow + 1 + off, min(deg - off, (uint32_t)kCandCap), 0);
+                    const uint32_t n = filter_unvisited(w, tags, (uint8_t)epoch, arow + 1 + off, min(deg - off, (uint32_t)kCandCap), 0,
+                                                        kBuild ? p.node_lo + qidx : 0xffffffffu);
                     cmps += n;
                     if (n) evaluate_candidates<kL2>(w, p, n, prefetch_adj);
                 }
@@ -405,12 +421,16 @@ __global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams 
             }
         }
 
-        // :2408-2418
-        if (w.size < p.k && lane == 0) atomicCAS(p.stats + 3, 0ull, ((unsigned long long)w.size << 32) | 1ull);
-        for (uint32_t i = lane; i < p.k; i += 32) {
-            const bool ok = i < w.size;
-            p.out_ids[(size_t)qidx * p.k + i] = ok ? (w.qi[i] & kIdMask) : 0xffffffffu;
-            p.out_dists[(size_t)qidx * p.k + i] = ok ? w.qd[i] : 0.f;
+        if (kBuild) {
+            if (lane == 0) p.exp_cnt[qidx] = min(hops, p.exp_cap);
+        } else {
+            // :2408-2418
+            if (w.size < p.k && lane == 0) atomicCAS(p.stats + 3, 0ull, ((unsigned long long)w.size << 32) | 1ull);
+            for (uint32_t i = lane; i < p.k; i += 32) {
+                const bool ok = i < w.size;
+                p.out_ids[(size_t)qidx * p.k + i] = ok ? (w.qi[i] & kIdMask) : 0xffffffffu;
+                p.out_dists[(size_t)qidx * p.k + i] = ok ? w.qd[i] : 0.f;
+            }
         }
         if (lane == 0) {
             if (p.out_cmps) p.out_cmps[qidx] = cmps;
@@ -444,7 +464,7 @@ uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L)
     return (b + 127u) & ~127u;
 }
 
-template <bool kL2, bool kBip>
+template <bool kL2, int kBip>
 int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
     auto kern = beam_search_kernel<kL2, kBip>;
     RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
@@ -501,10 +521,13 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
 }
 
 int launch_roargraph(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
-    return p.metric_l2 ? launch_t<true, false>(p, l, s) : launch_t<false, false>(p, l, s);
+    return p.metric_l2 ? launch_t<true, 0>(p, l, s) : launch_t<false, 0>(p, l, s);
 }
 int launch_bipartite(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
-    return p.metric_l2 ? launch_t<true, true>(p, l, s) : launch_t<false, true>(p, l, s);
+    return p.metric_l2 ? launch_t<true, 1>(p, l, s) : launch_t<false, 1>(p, l, s);
+}
+int launch_build_search(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    return p.metric_l2 ? launch_t<true, 2>(p, l, s) : launch_t<false, 2>(p, l, s);
 }
 
 }  // namespace rg

@@ -1,0 +1,89 @@
+"""Base-sharded search across the GPUs of one box: one process per GPU, every rank owns a slice of the base rows and
+its own RoarGraph over that slice, every query runs on every shard, and ONE all-gather of the per-shard top-k
+(distance, global id) lists followed by a k-way merge kernel yields the final top-k on every rank (SURVEY.md 8(e),
+BASELINE.json north_star).  The merge is the std::sort merge of compute_groundtruth.cpp:424-444 applied to search
+results: ascending (distance, id).
+
+torch.distributed is the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU tests); the merge itself is the
+CUDA kernel rg_topk_merge_dev — there is no CPU merge in the product.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import roargraph_b200 as rg
+
+
+def shard_range(nb: int, shard: int, n_shards: int):
+    """Rows [lo, hi) of shard `shard`: the same split compute_groundtruth uses for base parts, by equal counts."""
+    return shard * nb // n_shards, (shard + 1) * nb // n_shards
+
+
+def gather_topk(local_dists, local_ids, group=None):
+    """all-gather [nq, k] per-shard lists into [G, nq, k] tensors (same device/backend as the inputs)."""
+    import torch
+    import torch.distributed as dist
+
+    G = dist.get_world_size(group)
+    out_d = torch.empty((G,) + tuple(local_dists.shape), dtype=local_dists.dtype, device=local_dists.device)
+    out_i = torch.empty((G,) + tuple(local_ids.shape), dtype=local_ids.dtype, device=local_ids.device)
+    dist.all_gather_into_tensor(out_d, local_dists.contiguous(), group=group)
+    dist.all_gather_into_tensor(out_i, local_ids.contiguous(), group=group)
+    return out_d, out_i
+
+
+class ShardedRoarIndex:
+    """A RoarIndex over base rows [row_lo, row_lo + nd) of a larger base; search() returns GLOBAL ids merged over all
+    ranks of `group` (identical on every rank).  With a single rank it degenerates to the local search."""
+
+    def __init__(self, index: "rg.RoarIndex", row_lo: int = 0, group=None):
+        import torch.distributed as dist
+
+        self.index = index
+        self.row_lo = int(row_lo)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._buf = {}
+
+    def _scratch(self, nq, k, device):
+        import torch
+
+        key = (nq, k)
+        if key not in self._buf:
+            self._buf[key] = (torch.empty((nq, k), dtype=torch.int32, device=device),
+                              torch.empty((nq, k), dtype=torch.float32, device=device))
+        return self._buf[key]
+
+    def search_dev(self, d_q, k: int, L_pq: int, out_ids, out_dists, d_cmps=None, d_hops=None) -> int:
+        """Device tensors in/out on torch's current stream.  Returns the number of kernels launched."""
+        import torch
+
+        stream = torch.cuda.current_stream()
+        if self.world == 1:
+            self.index.search_dev(d_q, k, L_pq, out_ids, out_dists, d_cmps, d_hops, stream=stream)
+            if self.row_lo:
+                out_ids.add_(self.row_lo)
+                return 2
+            return 1
+        loc_i, loc_d = self._scratch(d_q.shape[0], k, d_q.device)
+        self.index.search_dev(d_q, k, L_pq, loc_i, loc_d, d_cmps, d_hops, stream=stream)
+        loc_i.add_(self.row_lo)  # local -> global ids, like start_id in compute_groundtruth.cpp:413
+        all_d, all_i = gather_topk(loc_d, loc_i, self.group)
+        rg.topk_merge_dev(all_d, all_i, out_dists, out_ids, stream=stream)
+        return 3
+
+    def search(self, queries: np.ndarray, k: int, L_pq: int):
+        """Host buffers in (ideally pinned), host numpy out: H2D, per-shard search, all-gather, merge, D2H."""
+        import torch
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        q = torch.from_numpy(queries)
+        d_q = q.to(dev, non_blocking=True)
+        nq = d_q.shape[0]
+        out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.search_dev(d_q, k, L_pq, out_i, out_d)
+        ids = out_i.cpu().numpy().view(np.uint32)
+        dists = out_d.cpu().numpy()
+        self.index.check(torch.cuda.current_stream())
+        return ids, dists
