@@ -53,7 +53,7 @@ struct SearchParams {
 };
 
 struct SearchLaunch {
-    uint32_t grid, block, smem_bytes, rows_per_batch, warps_per_cta;
+    uint32_t grid, block, smem_bytes, rows_per_batch, warps_per_cta, ctas_per_sm;
 };
 
 // Computes the launch geometry (and per-warp smem layout fields of `p`) for queue length L.

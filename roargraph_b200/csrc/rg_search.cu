@@ -302,8 +302,9 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 // kMode: 0 = SearchRoarGraph, 1 = SearchBipartiteGraph, 2 = SearchProjectionGraphInternal (the build's
 // connectivity-enhancement search, src/index_bipartite.cpp:1279-1350: the query is base row node_lo + ticket, that node
 // is never evaluated, the entry point IS marked visited, and the expanded nodes are the output).
-template <bool kL2, int kMode>
-__global__ void __launch_bounds__(128, 4) beam_search_kernel(const SearchParams p) {
+// kMinBlocks: resident CTAs per SM the register allocation is capped for (4 -> 104 regs, 6 -> 80, 8 -> 64; no spills).
+template <bool kL2, int kMode, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const SearchParams p) {
     constexpr bool kBipartite = kMode == 1;
     constexpr bool kBuild = kMode == 2;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -464,9 +465,9 @@ uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L)
     return (b + 127u) & ~127u;
 }
 
-template <bool kL2, int kBip>
-int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
-    auto kern = beam_search_kernel<kL2, kBip>;
+template <bool kL2, int kMode, int kMinBlocks>
+int launch_v(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    auto kern = beam_search_kernel<kL2, kMode, kMinBlocks>;
     RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
     RG_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), s));
     RG_CUDA(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s));
@@ -475,14 +476,21 @@ int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
     return RG_OK;
 }
 
+template <bool kL2, int kMode>
+int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    if (l.ctas_per_sm > 6) return launch_v<kL2, kMode, 8>(p, l, s);
+    if (l.ctas_per_sm > 4) return launch_v<kL2, kMode, 6>(p, l, s);
+    return launch_v<kL2, kMode, 4>(p, l, s);
+}
+
 }  // namespace
 
-uint32_t max_search_slots(int sm_count) { return (uint32_t)sm_count * 16u; }
+uint32_t max_search_slots(int sm_count) { return (uint32_t)sm_count * 32u; }
 
 int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slots) {
     const uint32_t dim = p.dim;
     p.row_stride_smem = dim + ((16u + 32u - (dim & 31u)) & 31u);  // stride % 32 == 16 -> conflict-free float4 reads
-    uint32_t R = env_u32("RG_ROWS_PER_BATCH", 16);
+    uint32_t R = env_u32("RG_ROWS_PER_BATCH", 8);
     if (R < 8) R = 8;
     if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
     R &= ~7u;
@@ -501,8 +509,9 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     }
     uint32_t ctas = kMaxSmemPerCta / (warps * wb + 1024u);
     if (ctas < 1) ctas = 1;
-    const uint32_t max_ctas = 16u / warps;
+    const uint32_t max_ctas = (warps == 4) ? 8u : 16u / warps;  // 8 x 128 threads x 64 registers fill the register file
     if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas == 7) ctas = 6;  // register variants exist for 4, 6 and 8 resident CTAs
     const uint32_t env_ctas = env_u32("RG_CTAS_PER_SM", 0);
     if (env_ctas && env_ctas < ctas) ctas = env_ctas;
     uint32_t grid = (uint32_t)sm_count * ctas;
@@ -517,6 +526,7 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     l.smem_bytes = warps * wb;
     l.rows_per_batch = R;
     l.warps_per_cta = warps;
+    l.ctas_per_sm = ctas;
     return RG_OK;
 }
 

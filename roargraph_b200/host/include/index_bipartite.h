@@ -1,0 +1,98 @@
+// efanna2e::IndexBipartite — host mirror of the reference's index object (include/index_bipartite.h:22-172) for the
+// B200 build.  Same constructor, loaders, search entry points, parameters and error behaviour; the work happens in
+// librg_b200.so (include/rg_b200.h), there is no CPU search path.
+//
+//   reference member (index_bipartite.h)                     here
+//   IndexBipartite(dim, n, Metric, Index*)              :27  same; creates nothing on the device yet
+//   LoadSearchNeededData / LoadVectorData               :62  fbin -> padded host rows (normalised for COSINE) -> HBM
+//   LoadProjectionGraph                                 :105 index file -> CSR -> fixed-stride adjacency in HBM
+//   Load / Save (bipartite graph)                       :29-30
+//   InitVisitedListPool(num_threads)                    :133 accepted, no-op (visited tags live on the device)
+//   SearchRoarGraph(query,k,qid,params,indices,dists)   :100 batch of one through SearchRoarGraphBatch
+//   SearchBipartiteGraph(...)                           :137 batch of one through SearchBipartiteGraphBatch
+//   LoadLearnBaseKNN                                    :109 reads the ids of the training queries' kNN file
+//   BuildRoarGraph(n_sq, sq, n_bp, bp, params)          :38  device build (rg_index_build_roargraph)
+//   SaveProjectionGraph                                 :103 same file format
+//   GetProjectionGraph                                  :113 host copy of the adjacency lists
+//   need_normalize                                      :145
+// New: SearchRoarGraphBatch / SearchBipartiteGraphBatch — the whole query batch crosses the boundary in one call,
+// where the reference's CLI runs `#pragma omp parallel for` over SearchRoarGraph (tests/test_search_roargraph.cpp:203).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "efanna2e/index.h"
+#include "efanna2e/util.h"
+
+struct rg_index;
+
+namespace efanna2e {
+
+class IndexBipartite : public Index {
+  typedef std::vector<std::vector<uint32_t>> CompactGraph;
+
+ public:
+  explicit IndexBipartite(const size_t dimension, const size_t n, Metric m, Index *initializer);
+  ~IndexBipartite() override;
+
+  void Save(const char *filename) override;  // bipartite graph: u32 npts, {u32 deg, u32 ids[deg]} * npts
+  void Load(const char *filename) override;
+  void Search(const float *query, const float *x, size_t k, const Parameters &parameters, unsigned *indices,
+              float *res_dists) override;
+  void Build(size_t n, const float *data, const Parameters &parameters) override;
+
+  void LoadVectorData(const char *base_file, const char *sampled_query_file);
+  inline void LoadSearchNeededData(const char *base_file, const char *sampled_query_file) {
+    LoadVectorData(base_file, sampled_query_file);
+  }
+  // Hand over base rows already in host memory (stride == GetDimension(), normalised for COSINE); copied to HBM.
+  void SetBaseData(const float *base, size_t n);
+
+  void LoadProjectionGraph(const char *filename);
+  void SaveProjectionGraph(const char *filename);
+  void LoadLearnBaseKNN(const char *filename);
+  void InitVisitedListPool(uint32_t num_threads) { (void)num_threads; }
+
+  void BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data, const Parameters &parameters);
+
+  std::pair<uint32_t, uint32_t> SearchRoarGraph(const float *query, size_t k, size_t &qid, const Parameters &parameters,
+                                                unsigned *indices, std::vector<float> &res_dists);
+  std::pair<uint32_t, uint32_t> SearchBipartiteGraph(const float *query, size_t k, size_t &qid,
+                                                     const Parameters &parameters, unsigned *indices,
+                                                     std::vector<float> &dists);
+  // queries: nq x GetDimension(); indices/dists: nq x k; cmps/hops: nq (may be null)
+  void SearchRoarGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters, unsigned *indices,
+                            float *dists, uint32_t *cmps, uint32_t *hops);
+  // init_ids: nq x n_init entry points, or null to draw them from `seed` (the reference draws 10 per query from an
+  // unseeded std::random_device, src/index_bipartite.cpp:287-294)
+  void SearchBipartiteGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
+                                 const uint32_t *init_ids, uint32_t n_init, uint64_t seed, unsigned *indices, float *dists,
+                                 uint32_t *cmps, uint32_t *hops);
+
+  CompactGraph &GetProjectionGraph();
+  CompactGraph &GetBipartiteGraph() { return bipartite_graph_; }
+  uint32_t GetProjectionEp() const { return projection_ep_; }
+  std::vector<std::vector<uint32_t>> &GetLearnBaseKNN() { return learn_base_knn_; }
+  // totals of the last batch (for the CLI's extra roofline columns)
+  void LastSearchStats(uint64_t &cmps, uint64_t &hops, uint64_t &adj_words) const;
+
+  Index *initializer_;
+  bool need_normalize = false;
+
+ protected:
+  void EnsureDeviceIndex();
+  void UploadProjectionGraph();
+  [[noreturn]] void Fail(int rc) const;
+
+  CompactGraph bipartite_graph_;
+  CompactGraph projection_graph_;
+  bool projection_host_valid_ = false;
+  std::vector<std::vector<uint32_t>> learn_base_knn_;
+  uint32_t projection_ep_ = 0;
+  float *owned_base_ = nullptr;
+  rg_index *dev_ = nullptr;
+};
+
+}  // namespace efanna2e

@@ -1,0 +1,291 @@
+// efanna2e::IndexBipartite over librg_b200.so.  File formats and error texts follow the reference
+// (src/index_bipartite.cpp there): LoadProjectionGraph :2097-2117, SaveProjectionGraph :2606-2619, Save/Load :2045-2071,
+// LoadLearnBaseKNN :2622-2642, LoadVectorData :2664-2695, "not enough results" :2408-2412.
+#include "index_bipartite.h"
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+
+#include "rg_b200.h"
+
+namespace efanna2e {
+
+namespace {
+int to_rg_metric(Metric m) {
+  switch (m) {
+    case L2: return RG_METRIC_L2;
+    case COSINE: return RG_METRIC_COSINE;
+    default: return RG_METRIC_INNER_PRODUCT;
+  }
+}
+
+void read_adjacency(std::ifstream &in, uint32_t npts, std::vector<std::vector<uint32_t>> &g, double &deg_sum) {
+  g.assign(npts, {});
+  deg_sum = 0;
+  for (uint32_t i = 0; i < npts; ++i) {
+    uint32_t d = 0;
+    in.read((char *)&d, 4);
+    if (!in) throw std::runtime_error("index file truncated");
+    g[i].resize(d);
+    in.read((char *)g[i].data(), (std::streamsize)d * 4);
+    deg_sum += d;
+  }
+}
+
+void to_csr(const std::vector<std::vector<uint32_t>> &g, std::vector<uint64_t> &row_off, std::vector<uint32_t> &nbrs) {
+  row_off.assign(g.size() + 1, 0);
+  for (size_t i = 0; i < g.size(); ++i) row_off[i + 1] = row_off[i] + g[i].size();
+  nbrs.resize(row_off.back());
+  for (size_t i = 0; i < g.size(); ++i)
+    if (!g[i].empty()) memcpy(nbrs.data() + row_off[i], g[i].data(), g[i].size() * 4);
+}
+}  // namespace
+
+IndexBipartite::IndexBipartite(const size_t dimension, const size_t n, Metric m, Index *initializer)
+    : Index(dimension, n, m), initializer_(initializer) {
+  bipartite_ = true;
+  if (m == COSINE) need_normalize = true;
+}
+
+IndexBipartite::~IndexBipartite() {
+  if (dev_) rg_index_destroy(dev_);
+  free(owned_base_);
+}
+
+void IndexBipartite::Fail(int rc) const {
+  const std::string msg = rg_last_error();
+  if (rc == RG_EINVAL) throw std::invalid_argument(msg);
+  throw std::runtime_error(msg);
+}
+
+void IndexBipartite::EnsureDeviceIndex() {
+  if (dev_) return;
+  if (!data_bp_) throw std::runtime_error("base data not loaded");
+  int rc = rg_index_create(&dev_, data_bp_, nd_, (uint32_t)dimension_, to_rg_metric(metric_), 0);
+  if (rc != RG_OK) Fail(rc);
+}
+
+void IndexBipartite::SetBaseData(const float *base, size_t n) {
+  if (dev_) {
+    rg_index_destroy(dev_);
+    dev_ = nullptr;
+  }
+  data_bp_ = base;
+  nd_ = n;
+  EnsureDeviceIndex();
+}
+
+void IndexBipartite::LoadVectorData(const char *base_file, const char *sampled_query_file) {
+  uint32_t base_num = 0, base_dim = 0, sq_num = 0, q_dim = 0;
+  load_meta<float>(base_file, base_num, base_dim);
+  if (strlen(sampled_query_file) != 0) {
+    load_meta<float>(sampled_query_file, sq_num, q_dim);
+    if (base_dim != q_dim) throw std::runtime_error("base and query dimension mismatch");
+  }
+  float *base = nullptr;
+  load_data<float>(base_file, base_num, base_dim, base);
+  unsigned padded = base_dim;
+  base = data_align(base, base_num, padded);
+  if (padded != dimension_) {
+    free(base);
+    throw std::runtime_error("base dimension (padded to x8) does not match the index dimension");
+  }
+  if (need_normalize) {
+    std::cout << "Normalizing base data" << std::endl;
+    for (size_t i = 0; i < base_num; ++i) normalize<float>(base + i * (uint64_t)padded, padded);
+  }
+  free(owned_base_);
+  owned_base_ = base;
+  nd_sq_ = sq_num;
+  SetBaseData(base, base_num);
+}
+
+void IndexBipartite::UploadProjectionGraph() {
+  EnsureDeviceIndex();
+  std::vector<uint64_t> row_off;
+  std::vector<uint32_t> nbrs;
+  if (projection_graph_.size() != nd_) throw std::runtime_error("projection graph size does not match the base size");
+  to_csr(projection_graph_, row_off, nbrs);
+  int rc = rg_index_set_graph(dev_, projection_ep_, row_off.data(), nbrs.data());
+  if (rc != RG_OK) Fail(rc);
+  projection_host_valid_ = true;
+}
+
+void IndexBipartite::LoadProjectionGraph(const char *filename) {
+  std::ifstream in(filename, std::ios::binary);
+  if (!in.is_open()) throw std::runtime_error(std::string("cannot open index file ") + filename);
+  uint32_t npts = 0;
+  in.read((char *)&projection_ep_, 4);
+  std::cout << "Projection graph, ep: " << projection_ep_ << std::endl;
+  in.read((char *)&npts, 4);
+  double deg = 0;
+  read_adjacency(in, npts, projection_graph_, deg);
+  std::cout << "Projection graph, avg_degree: " << deg / npts << std::endl;
+  UploadProjectionGraph();
+}
+
+IndexBipartite::CompactGraph &IndexBipartite::GetProjectionGraph() {
+  if (!projection_host_valid_ && dev_) {
+    uint64_t nnz = 0;
+    uint32_t ep = 0, md = 0;
+    int rc = rg_index_graph_size(dev_, &nnz, &ep, &md);
+    if (rc == RG_OK) {
+      std::vector<uint64_t> row_off(nd_ + 1);
+      std::vector<uint32_t> nbrs(nnz);
+      rc = rg_index_get_graph(dev_, row_off.data(), nbrs.data());
+      if (rc != RG_OK) Fail(rc);
+      projection_graph_.assign(nd_, {});
+      for (size_t i = 0; i < nd_; ++i)
+        projection_graph_[i].assign(nbrs.begin() + row_off[i], nbrs.begin() + row_off[i + 1]);
+      projection_ep_ = ep;
+      projection_host_valid_ = true;
+    }
+  }
+  return projection_graph_;
+}
+
+void IndexBipartite::SaveProjectionGraph(const char *filename) {
+  CompactGraph &g = GetProjectionGraph();
+  std::ofstream out(filename, std::ios::binary | std::ios::out);
+  if (!out.is_open()) throw std::runtime_error("cannot open file");
+  const uint32_t npts = (uint32_t)g.size();
+  out.write((const char *)&projection_ep_, 4);
+  out.write((const char *)&npts, 4);
+  for (uint32_t i = 0; i < npts; ++i) {
+    const uint32_t d = (uint32_t)g[i].size();
+    out.write((const char *)&d, 4);
+    out.write((const char *)g[i].data(), (std::streamsize)d * 4);
+  }
+}
+
+void IndexBipartite::Save(const char *filename) {
+  std::ofstream out(filename, std::ios::binary | std::ios::out);
+  if (!out.is_open()) throw std::runtime_error("cannot open file");
+  const uint32_t npts = (uint32_t)bipartite_graph_.size();
+  out.write((const char *)&npts, 4);
+  for (uint32_t i = 0; i < npts; ++i) {
+    const uint32_t d = (uint32_t)bipartite_graph_[i].size();
+    out.write((const char *)&d, 4);
+    out.write((const char *)bipartite_graph_[i].data(), (std::streamsize)d * 4);
+  }
+}
+
+void IndexBipartite::Load(const char *filename) {
+  std::ifstream in(filename, std::ios::binary);
+  if (!in.is_open()) throw std::runtime_error(std::string("cannot open index file ") + filename);
+  uint32_t npts = 0;
+  in.read((char *)&npts, 4);
+  double deg = 0;
+  read_adjacency(in, npts, bipartite_graph_, deg);
+  EnsureDeviceIndex();
+  std::vector<uint64_t> row_off;
+  std::vector<uint32_t> nbrs;
+  to_csr(bipartite_graph_, row_off, nbrs);
+  int rc = rg_index_set_bipartite(dev_, npts, row_off.data(), nbrs.data());
+  if (rc != RG_OK) Fail(rc);
+}
+
+void IndexBipartite::LoadLearnBaseKNN(const char *filename) {
+  std::ifstream in(filename, std::ios::binary);
+  if (!in.is_open()) throw std::runtime_error("cannot open file");
+  uint32_t npts = 0, k_dim = 0;
+  in.read((char *)&npts, 4);
+  in.read((char *)&k_dim, 4);
+  std::cout << "learn base knn npts: " << npts << ", k_dim: " << k_dim << std::endl;
+  learn_base_knn_.assign(npts, {});
+  std::vector<uint32_t> block((size_t)npts * k_dim);
+  in.read((char *)block.data(), (std::streamsize)block.size() * 4);
+  if (!in) throw std::runtime_error("learn-base kNN file truncated");
+  for (uint32_t i = 0; i < npts; ++i) learn_base_knn_[i].assign(block.begin() + (size_t)i * k_dim, block.begin() + (size_t)(i + 1) * k_dim);
+}
+
+void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data,
+                                    const Parameters &parameters) {
+  std::cout << "start build bipartite index" << std::endl;
+  (void)sq_data;  // the reference never reads the training vectors either, only their kNN lists (:1063)
+  const uint32_t M_sq = parameters.Get<uint32_t>("M_sq");
+  const uint32_t M_pjbp = parameters.Get<uint32_t>("M_pjbp");
+  const uint32_t L_pjpq = parameters.Get<uint32_t>("L_pjpq");
+  if (learn_base_knn_.empty()) throw std::runtime_error("LoadLearnBaseKNN must be called before BuildRoarGraph");
+  if (need_normalize) {
+    std::cout << "normalizing base data" << std::endl;
+    float *d = const_cast<float *>(bp_data);
+    for (size_t i = 0; i < n_bp; ++i) normalize(d + i * dimension_, dimension_);
+  }
+  nd_sq_ = n_sq;
+  SetBaseData(bp_data, n_bp);
+  const size_t nsq = learn_base_knn_.size();
+  size_t stride = 0;
+  for (auto &r : learn_base_knn_) stride = std::max(stride, r.size());
+  std::vector<uint32_t> flat(nsq * stride, 0xffffffffu);
+  for (size_t i = 0; i < nsq; ++i) memcpy(flat.data() + i * stride, learn_base_knn_[i].data(), learn_base_knn_[i].size() * 4);
+  std::cout << "begin link projection" << std::endl;
+  int rc = rg_index_build_roargraph(dev_, flat.data(), 0, nsq, (uint32_t)stride, std::min<uint32_t>(M_sq, (uint32_t)stride),
+                                    M_pjbp, L_pjpq, parameters.Get<uint32_t>("build_rounds", 0u));
+  if (rc != RG_OK) Fail(rc);
+  projection_host_valid_ = false;
+  uint64_t nnz = 0;
+  uint32_t md = 0;
+  rg_index_graph_size(dev_, &nnz, &projection_ep_, &md);
+  std::cout << "projection ep: " << projection_ep_ << std::endl;
+  std::cout << "total degree: " << nnz << std::endl;
+  std::cout << "Projection degree avg: " << (double)nnz / (double)n_bp << std::endl;
+  std::cout << "Projection degree max: " << md << std::endl;
+  has_built = true;
+}
+
+void IndexBipartite::Build(size_t n, const float *data, const Parameters &parameters) {
+  BuildRoarGraph(nd_sq_, nullptr, n, data, parameters);
+}
+
+void IndexBipartite::SearchRoarGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
+                                          unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
+  const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");
+  if (!dev_) throw std::runtime_error("index not loaded");
+  int rc = rg_search_roargraph(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, indices, dists, cmps, hops);
+  if (rc != RG_OK) Fail(rc);
+}
+
+std::pair<uint32_t, uint32_t> IndexBipartite::SearchRoarGraph(const float *query, size_t k, size_t &qid,
+                                                              const Parameters &parameters, unsigned *indices,
+                                                              std::vector<float> &res_dists) {
+  (void)qid;
+  uint32_t cmps = 0, hops = 0;
+  res_dists.resize(k);
+  SearchRoarGraphBatch(query, 1, k, parameters, indices, res_dists.data(), &cmps, &hops);
+  return {cmps, hops};
+}
+
+void IndexBipartite::SearchBipartiteGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
+                                               const uint32_t *init_ids, uint32_t n_init, uint64_t seed,
+                                               unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
+  const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");
+  if (!dev_) throw std::runtime_error("index not loaded");
+  int rc = rg_search_bipartite(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, init_ids, n_init, seed, indices, dists, cmps, hops);
+  if (rc != RG_OK) Fail(rc);
+}
+
+std::pair<uint32_t, uint32_t> IndexBipartite::SearchBipartiteGraph(const float *query, size_t k, size_t &qid,
+                                                                   const Parameters &parameters, unsigned *indices,
+                                                                   std::vector<float> &dists) {
+  uint32_t cmps = 0, hops = 0;
+  dists.resize(k);
+  SearchBipartiteGraphBatch(query, 1, k, parameters, nullptr, 10, (uint64_t)qid, indices, dists.data(), &cmps, &hops);
+  return {cmps, hops};
+}
+
+void IndexBipartite::Search(const float *query, const float *x, size_t k, const Parameters &parameters, unsigned *indices,
+                            float *res_dists) {
+  (void)x;  // the Index virtual has no call site in the reference either ("dead/legacy search")
+  SearchRoarGraphBatch(query, 1, k, parameters, indices, res_dists, nullptr, nullptr);
+}
+
+void IndexBipartite::LastSearchStats(uint64_t &cmps, uint64_t &hops, uint64_t &adj_words) const {
+  cmps = hops = adj_words = 0;
+  if (dev_) rg_search_last_stats(dev_, &cmps, &hops, &adj_words);
+}
+
+}  // namespace efanna2e
