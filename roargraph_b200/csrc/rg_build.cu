@@ -516,7 +516,7 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
     sp.adj = supply;
     sp.adj_stride = sstride;
     sp.ep = ep;
-    sp.n_init = 1;
+    sp.n_init = 0;
     sp.exp_ids = b_exp_ids.as<uint32_t>();
     sp.exp_dists = b_exp_d.as<float>();
     sp.exp_cnt = b_exp_cnt.as<uint32_t>();

@@ -328,7 +328,9 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
         p.adj_stride = idx->adj_stride;
         p.ep = idx->ep;
         const char *pf = getenv("RG_PREFETCH_ADJ");
-        p.n_init = (pf && pf[0] == '0') ? 0u : 1u;  // doubles as the adjacency-prefetch switch
+        // doubles as the adjacency-prefetch switch; off by default: at 24 resident warps per SM the extra L2 fills cost
+        // more DRAM bandwidth than the shorter dependent read saves (profiles/r1_tune_10M.csv)
+        p.n_init = (pf && pf[0] == '1') ? 1u : 0u;
     }
     p.queries = d_q;
     p.out_ids = d_ids;
