@@ -121,6 +121,15 @@ int ensure_device_ready();
 int ensure_tags(rg_index *idx, uint32_t slots);
 uint32_t affordable_slots(rg_index *idx);
 
+// tensor-core candidate filter of the kNN (rg_knn_tc.cu)
+bool knn_tc_supported(uint32_t dim);
+uint32_t knn_tc_pitch(uint32_t dim);
+int knn_tc_convert(const float *x, uint64_t n, uint32_t dim, void *out_bf16, float *sq, cudaStream_t s);
+int knn_tc_max_norm(const float *sq, uint64_t n, float *d_out, cudaStream_t s);
+int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
+                  int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
+                  uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s);
+
 // BuildRoarGraph (rg_build.cu)
 int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, uint32_t knn_stride, uint32_t M_sq,
                            uint32_t M, uint32_t L, uint32_t n_rounds, cudaStream_t s);

@@ -120,13 +120,42 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_gemm_filter_kernel(
 
 // Fold candidates into the running sorted top-K of each query (one CTA per query), update tau, reset the counter.
 // top: nq x K packed words ascending (unused tail = ~0ull).
+// With `rr.base != nullptr` the candidates carry only a base id (tensor-core filter, rg_knn_tc.cu) and their exact fp32
+// internal distance is computed here first: one warp per candidate, query row staged in shared memory.
+struct Rerank {
+    const float *base, *queries;  // fp32 rows, row stride == dim
+    const float *qn, *bn;         // squared norms (L2)
+    uint32_t dim;
+    int metric_l2;
+};
+
 __global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t K, unsigned long long *__restrict__ cand,
-                                 uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n) {
+                                 uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n,
+                                 const Rerank rr) {
     extern __shared__ unsigned long long sk[];
     const uint64_t q = blockIdx.x;
     uint32_t n = cand_cnt[q];
     if (n > cap) n = cap;
     if (n == 0) return;
+    if (rr.base) {
+        float *sq = reinterpret_cast<float *>(sk + sort_n);  // dim floats after the sort buffer
+        for (uint32_t j = threadIdx.x; j < rr.dim; j += blockDim.x) sq[j] = rr.queries[q * rr.dim + j];
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const float qq = rr.metric_l2 ? rr.qn[q] : 0.f;
+        for (uint32_t i = warp; i < n; i += nwarps) {
+            const uint32_t b = (uint32_t)cand[q * cap + i];
+            const float *br = rr.base + (uint64_t)b * rr.dim;
+            float acc = 0.f;
+            for (uint32_t j = lane; j < rr.dim; j += 32) acc = fmaf(sq[j], __ldg(br + j), acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const float d = rr.metric_l2 ? (-2.0f * acc + rr.bn[b]) + qq : -acc;
+                cand[q * cap + i] = ((unsigned long long)f2ord(d) << 32) | b;
+            }
+        }
+        __syncthreads();
+    }
     // smallest power of two holding n + K
     uint32_t m = 1;
     while (m < n + K) m <<= 1;
@@ -217,6 +246,12 @@ struct Scratch {
 
 }  // namespace
 
+static bool use_tensor_cores(uint32_t dim) {
+    const char *m = getenv("RG_KNN_MODE");
+    if (m && m[0] == 's') return false;  // RG_KNN_MODE=simt: the fp32 SIMT tile (also taken for dim > 512)
+    return knn_tc_supported(dim);
+}
+
 int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
                int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s) {
     if (!d_base || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
@@ -228,16 +263,18 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     const int metric_l2 = (metric == RG_METRIC_L2 || cosine) ? 1 : 0;
     if (!metric_l2 && metric != RG_METRIC_INNER_PRODUCT) { set_error("rg_knn: unknown metric"); return RG_EINVAL; }
 
+    const bool tc = use_tensor_cores(dim);
     const uint32_t cap = std::max<uint32_t>(2048u, 4u * K);
+    const uint64_t chunk0 = tc ? (cap / 256u) * 256u : cap;  // tensor-core tiles are 256 base rows
     uint32_t sort_n = 1;
     while (sort_n < cap + K) sort_n <<= 1;
     // query batches so that the candidate lists stay within ~2 GiB
     const uint64_t qb_max = std::max<uint64_t>(TQ, ((2ull << 30) / (cap * 8ull)) / TQ * TQ);
 
-    Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf;
+    Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf, s_b16, s_q16, s_max;
     float *bn = nullptr, *qn = nullptr;
     const float *B = d_base, *Q = d_queries;
-    if (metric_l2) {
+    if (metric_l2 || tc) {  // the tensor-core filter needs the norms for its error bound even for inner product
         RG_CUDA(cudaMalloc(&s_bn.p, nb * sizeof(float)));
         RG_CUDA(cudaMalloc(&s_qn.p, nq * sizeof(float)));
         bn = (float *)s_bn.p;
@@ -256,6 +293,29 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
         }
     }
     const uint64_t qb_alloc = std::min<uint64_t>(nq, qb_max);
+    float bmax = 0.f;
+    if (tc) {
+        const uint32_t kp = knn_tc_pitch(dim);
+        RG_CUDA(cudaMalloc(&s_b16.p, nb * kp * 2));
+        RG_CUDA(cudaMalloc(&s_q16.p, qb_alloc * kp * 2));
+        RG_CUDA(cudaMalloc(&s_max.p, sizeof(float)));
+        int rc = knn_tc_convert(B, nb, dim, s_b16.p, nullptr, s);
+        if (rc != RG_OK) return rc;
+        if ((rc = knn_tc_max_norm(bn, nb, (float *)s_max.p, s)) != RG_OK) return rc;
+        float m2 = 0.f;
+        RG_CUDA(cudaMemcpyAsync(&m2, s_max.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+        RG_CUDA(cudaStreamSynchronize(s));
+        bmax = sqrtf(m2);
+    }
+    Rerank rr{};
+    if (tc) {
+        rr.base = B;
+        rr.qn = qn;
+        rr.bn = bn;
+        rr.dim = dim;
+        rr.metric_l2 = metric_l2;
+    }
+    const size_t merge_smem = (size_t)sort_n * 8 + (tc ? (size_t)dim * 4 : 0);
     RG_CUDA(cudaMalloc(&s_top.p, qb_alloc * K * sizeof(unsigned long long)));
     RG_CUDA(cudaMalloc(&s_cand.p, qb_alloc * cap * sizeof(unsigned long long)));
     RG_CUDA(cudaMalloc(&s_cnt.p, qb_alloc * sizeof(uint32_t)));
@@ -264,23 +324,35 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     unsigned long long *top = (unsigned long long *)s_top.p, *cand = (unsigned long long *)s_cand.p;
     uint32_t *cnt = (uint32_t *)s_cnt.p, *ovf = (uint32_t *)s_ovf.p;
     float *tau = (float *)s_tau.p;
-    RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sort_n * 8)));
+    RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
 
     for (uint64_t qs = 0; qs < nq; qs += qb_max) {
         const uint64_t nqb = std::min<uint64_t>(qb_max, nq - qs);
+        if (tc) {
+            int rc = knn_tc_convert(Q + qs * dim, nqb, dim, s_q16.p, nullptr, s);
+            if (rc != RG_OK) return rc;
+            rr.queries = Q + qs * dim;
+            rr.qn = qn + qs;
+        }
         for (int attempt = 0; attempt < 2; ++attempt) {
             // attempt 0: chunks double in size (expected survivors per chunk ~K); attempt 1 (after a candidate-list
             // overflow): every chunk has at most `cap` rows, which cannot overflow.
             const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
             knn_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, s>>>(top, nqb * K, tau, cnt, nqb);
             RG_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), s));
-            uint64_t lo = 0, csize = cap;
+            uint64_t lo = 0, csize = chunk0;
             while (lo < nb) {
                 const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
-                dim3 grid((unsigned)((hi - lo + TB - 1) / TB), (unsigned)((nqb + TQ - 1) / TQ));
-                knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
-                                                                    bn, metric_l2, tau, cand, cnt, cap, ovf);
-                knn_merge_kernel<<<(unsigned)nqb, 256, sort_n * 8, s>>>(top, K, cand, cnt, cap, tau, sort_n);
+                if (tc) {
+                    int rc = knn_tc_filter(s_q16.p, nqb, s_b16.p, nb, dim, lo, hi, metric_l2, tau, qn + qs, bn, bmax, cand, cnt, cap,
+                                           ovf, sm_count(), s);
+                    if (rc != RG_OK) return rc;
+                } else {
+                    dim3 grid((unsigned)((hi - lo + TB - 1) / TB), (unsigned)((nqb + TQ - 1) / TQ));
+                    knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
+                                                                        bn, metric_l2, tau, cand, cnt, cap, ovf);
+                }
+                knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr);
                 if (attempt == 0 && lo > 0) csize = std::min<uint64_t>(csize * 2, 1ull << 22);
                 lo = hi;
             }

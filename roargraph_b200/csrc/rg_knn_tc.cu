@@ -1,0 +1,421 @@
+// rg_knn_tc.cu — tensor-core candidate filter of the brute-force kNN (exact_knn, compute_groundtruth.cpp:126-248 of
+// the reference's vendored DiskANN): Q x B^T on tcgen05 (bf16 operands, fp32 accumulation in TMEM), TMA-staged operands,
+// and an epilogue that never writes the score tile anywhere — it only compares each score with the query's running
+// K-th best distance (widened by a rigorous bf16 error bound) and appends the rare survivors to the per-query
+// candidate list.  The exact fp32 distance of every survivor is recomputed by the merge kernel (rg_knn.cu), so the
+// returned neighbours and distances are those of an fp32 computation.
+//
+// One CTA = 128 queries (UMMA M = 128) x a range of 256-row base tiles (UMMA N = 256), 192 threads:
+//   warp 0      TMA producer: the query tile once (resident for the CTA's lifetime), then a ring of 64-column base
+//               k-blocks (32 KB each, 128B-swizzled, K-major)
+//   warp 1      MMA issuer: one elected lane, tcgen05.mma.cta_group::1.kind::f16, 13 k-steps of 16 for d = 200;
+//               tcgen05.commit releases ring stages and publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time from one of TWO 256-column accumulators (all 512
+//               TMEM columns), so the scan of tile t overlaps the MMAs of tile t+1.  Thread = query row: its threshold
+//               lives in a register.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdio>
+
+#include "rg_internal.h"
+
+namespace rg {
+namespace {
+
+constexpr int kBlockM = 128;   // queries per CTA
+constexpr int kBlockN = 256;   // base rows per tile
+constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytesPerKb = kBlockM * kBlockK * 2;  // 16 KB
+constexpr uint32_t kBBytesPerKb = kBlockN * kBlockK * 2;  // 32 KB
+constexpr int kMaxKb = 8;      // dim <= 512
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of the warp's TMEM lane quadrant
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); version 1 (sm_100);
+// layout type 2 = SWIZZLE_128B.  The tile base must be 1024-byte aligned; a k-step of 16 bf16 advances the start by 32 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+struct TcParams {
+    uint64_t nq;            // queries in this batch (rows of the A tensor map)
+    uint64_t nb;            // base rows (rows of the B tensor map)
+    uint32_t num_kb;        // 64-column k-blocks
+    uint32_t ksteps_last;   // k-steps of 16 in the last k-block
+    uint32_t stages;        // ring depth (k-blocks of B)
+    uint32_t tile_lo, tile_hi;  // base tiles [tile_lo, tile_hi) of this chunk
+    uint32_t tiles_per_cta;
+    int metric_l2;
+    const float *tau;       // running K-th best internal distance per query
+    const float *qn;        // ||q||^2 (exact fp32)
+    const float *bn;        // ||b||^2
+    float bmax;             // max_b ||b||
+    unsigned long long *cand;
+    uint32_t *cand_cnt;
+    uint32_t cap;
+    uint32_t *overflow;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                                     const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A: num_kb x 16 KB][B ring: stages x 32 KB][bn: 2 x 256 floats][barriers][tmem ptr]
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + (size_t)p.num_kb * kABytesPerKb;
+    float *s_bn = reinterpret_cast<float *>(sB + (size_t)p.stages * kBBytesPerKb);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_bn + 2 * kBlockN);
+    // bars: [0] a_full, [1..1+S) full, [1+S..1+2S) empty, then tmem_full[2], tmem_empty[2]
+    const uint32_t S = p.stages;
+    const uint32_t bar_a = smem_u32(bars);
+    const uint32_t bar_full = bar_a + 8;
+    const uint32_t bar_empty = bar_full + 8 * S;
+    const uint32_t bar_tfull = bar_empty + 8 * S;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 1 + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t q0 = (uint64_t)blockIdx.x * kBlockM;
+    const uint32_t t_begin = p.tile_lo + blockIdx.y * p.tiles_per_cta;
+    const uint32_t t_end = min(p.tile_hi, t_begin + p.tiles_per_cta);
+    const uint32_t n_tiles = t_end > t_begin ? t_end - t_begin : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        for (uint32_t s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators); this warp also frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0 && n_tiles) {
+            // query tile, resident
+            mbar_expect_tx(bar_a, p.num_kb * kABytesPerKb);
+            for (uint32_t kb = 0; kb < p.num_kb; ++kb)
+                tma_load_2d(smem_u32(sA + (size_t)kb * kABytesPerKb), &map_q, bar_a, (int)(kb * kBlockK), (int)q0);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t_begin; t < t_end; ++t) {
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, kBBytesPerKb);
+                    tma_load_2d(smem_u32(sB + (size_t)stage * kBBytesPerKb), &map_b, bar_full + 8 * stage, (int)(kb * kBlockK),
+                                (int)(t * kBlockN));
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && n_tiles) {
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t i = 0; i < n_tiles; ++i) {
+                const uint32_t buf = i & 1;
+                mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * kBlockN;
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + (size_t)kb * kABytesPerKb));
+                    const uint64_t b_desc = umma_desc_sw128(smem_u32(sB + (size_t)stage * kBBytesPerKb));
+                    const uint32_t nk = (kb == p.num_kb - 1) ? p.ksteps_last : (uint32_t)(kBlockK / kUmmaK);
+                    for (uint32_t k = 0; k < nk; ++k)
+                        tc_mma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs have read it
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(bar_tfull + 8 * buf);  // accumulator complete
+            }
+        }
+    } else {
+        // epilogue: TMEM lane quadrant = warp id % 4; this thread owns query row `row`
+        const uint32_t quad = (uint32_t)warp & 3u;
+        const uint32_t row = quad * 32 + lane;
+        const uint64_t q = q0 + row;
+        const bool q_ok = q < p.nq;
+        const int epi_tid = threadIdx.x - 64;  // 0..127
+        // keep a score iff its exact distance can still be below tau:  |dot_bf16 - dot| <= E
+        float theta = INFINITY;  // rows past the batch never pass
+        if (q_ok) {
+            const float t = p.tau[q];
+            const float qq = p.qn[q];
+            const float E = 1.01f * 0.0078125f * sqrtf(qq) * p.bmax;  // (2u + u^2) ||q|| ||b||, u = 2^-8, with slack
+            if (p.metric_l2) theta = (qq - t) - 2.f * E;                 // keep iff 2 dot - ||b||^2 > theta
+            else theta = (-t) - E;                                      // keep iff dot > theta
+            if (t == INFINITY) theta = -INFINITY;
+        }
+        unsigned long long *my_cand = p.cand + q * p.cap;
+        for (uint32_t i = 0; i < n_tiles; ++i) {
+            const uint32_t buf = i & 1;
+            const uint32_t tile = t_begin + i;
+            const uint64_t col0 = (uint64_t)tile * kBlockN;
+            if (p.metric_l2) {
+                // ||b||^2 of this tile's 256 rows -> shared (double-buffered with the accumulators)
+                for (int j = epi_tid; j < kBlockN; j += 128) {
+                    const uint64_t b = col0 + j;
+                    s_bn[buf * kBlockN + j] = b < p.nb ? __ldg(p.bn + b) : 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kBlockN;
+#pragma unroll 1
+            for (uint32_t c = 0; c < kBlockN / 32; ++c) {
+                uint32_t r[32];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after a divergent survivor scan
+                tc_ld32(taddr + c * 32, r);
+                float v[32];
+                if (p.metric_l2) {
+                    const float *bn = s_bn + buf * kBlockN + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(2.f, __uint_as_float(r[j]), -bn[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                }
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                if (m > theta) {  // rare once tau has tightened
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (v[j] > theta) {
+                            const uint64_t b = col0 + c * 32 + j;
+                            if (b < p.nb) {
+                                const uint32_t slot = atomicAdd(p.cand_cnt + q, 1u);
+                                if (slot < p.cap) my_cand[slot] = (unsigned long long)(uint32_t)b;
+                                else *p.overflow = 1u;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// fp32 rows -> bf16 rows of pitch kp (zero padded) + exact fp32 squared norms; one warp per row
+__global__ void to_bf16_kernel(const float *x, uint64_t n, uint32_t dim, uint32_t kp, __nv_bfloat16 *out, float *sq) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float *r = x + row * dim;
+    __nv_bfloat16 *o = out + row * kp;
+    float s = 0.f;
+    for (uint32_t j = lane; j < kp; j += 32) {
+        const float v = j < dim ? r[j] : 0.f;
+        s = fmaf(v, v, s);
+        o[j] = __float2bfloat16_rn(v);
+    }
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0 && sq) sq[row] = s;
+}
+
+__global__ void max_norm_kernel(const float *sq, uint64_t n, float *out) {
+    float m = 0.f;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = fmaxf(m, sq[i]);
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));  // non-negative floats order as ints
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint32_t kp, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return RG_ECUDA; }
+    const cuuint64_t dims[2] = {kp, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        set_error(buf);
+        return RG_ECUDA;
+    }
+    return RG_OK;
+}
+
+}  // namespace
+
+bool knn_tc_supported(uint32_t dim) { return dim >= 8 && ((dim + 7) / 8 * 8) <= (uint32_t)(kMaxKb * kBlockK) && encode_fn() != nullptr; }
+
+uint32_t knn_tc_pitch(uint32_t dim) { return (dim + 7) / 8 * 8; }
+
+int knn_tc_convert(const float *x, uint64_t n, uint32_t dim, void *out_bf16, float *sq, cudaStream_t s) {
+    to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(x, n, dim, knn_tc_pitch(dim), reinterpret_cast<__nv_bfloat16 *>(out_bf16), sq);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+int knn_tc_max_norm(const float *sq, uint64_t n, float *d_out, cudaStream_t s) {
+    RG_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float), s));
+    max_norm_kernel<<<296, 256, 0, s>>>(sq, n, d_out);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// One chunk [row_lo, row_hi) of the base (both multiples of 256, or row_hi == nb) against one query batch.
+int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
+                  int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
+                  uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s) {
+    const uint32_t kp = knn_tc_pitch(dim);
+    CUtensorMap map_q, map_b;
+    int rc = make_map(&map_q, q_bf16, nq, kp, kBlockM);
+    if (rc != RG_OK) return rc;
+    rc = make_map(&map_b, b_bf16, nb, kp, kBlockN);
+    if (rc != RG_OK) return rc;
+    TcParams p{};
+    p.nq = nq;
+    p.nb = nb;
+    p.num_kb = (kp + kBlockK - 1) / kBlockK;
+    p.ksteps_last = ((kp - (p.num_kb - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
+    const size_t fixed = (size_t)p.num_kb * kABytesPerKb + 2 * kBlockN * 4 + 512 + 1024;
+    const size_t budget = 227 * 1024;
+    uint32_t stages = (uint32_t)((budget - fixed) / kBBytesPerKb);
+    if (stages > 6) stages = 6;
+    if (stages < 2) { set_error("rg_knn: dimension too large for the tensor-core path"); return RG_EINVAL; }
+    p.stages = stages;
+    p.tile_lo = (uint32_t)(row_lo / kBlockN);
+    p.tile_hi = (uint32_t)((row_hi + kBlockN - 1) / kBlockN);
+    const uint32_t tiles = p.tile_hi - p.tile_lo;
+    const uint32_t q_tiles = (uint32_t)((nq + kBlockM - 1) / kBlockM);
+    uint32_t splits = 1;
+    if (q_tiles < 2u * (uint32_t)sm_count) splits = std::min<uint32_t>(tiles, (2u * (uint32_t)sm_count + q_tiles - 1) / q_tiles);
+    p.tiles_per_cta = (tiles + splits - 1) / splits;
+    splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    p.metric_l2 = metric_l2;
+    p.tau = tau;
+    p.qn = qn;
+    p.bn = bn;
+    p.bmax = bmax;
+    p.cand = cand;
+    p.cand_cnt = cand_cnt;
+    p.cap = cap;
+    p.overflow = overflow;
+    const size_t smem = fixed + (size_t)stages * kBBytesPerKb;
+    RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(q_tiles, splits);
+    knn_tc_filter_kernel<<<grid, kThreads, smem, s>>>(map_q, map_b, p);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+}  // namespace rg

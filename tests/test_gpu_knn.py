@@ -9,6 +9,13 @@ from test_oracle_golden import check_knn
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tc", "simt"], autouse=True)
+def knn_mode(request, monkeypatch):
+    """Every test runs through both candidate filters: the tcgen05 bf16 tile (default) and the fp32 SIMT tile."""
+    monkeypatch.setenv("RG_KNN_MODE", request.param)
+    return request.param
+
+
 def test_knn_golden(golden):
     K = golden.z["gt_ids"].shape[1]
     ids, dists = rg.knn(golden.base_raw, golden.test_raw, K, golden.metric)
@@ -64,3 +71,25 @@ def test_topk_merge():
     order = np.lexsort((alli, alld), axis=1)[:, :K]
     assert (np.take_along_axis(alld, order, 1) == od.cpu().numpy()).all()
     assert (np.take_along_axis(alli, order, 1) == oi.cpu().numpy().view(np.uint32)).all()
+
+
+def test_knn_tensor_core_matches_simt_at_scale(monkeypatch):
+    """300k x 200d base, 3000 queries, K=100: the bf16 tensor-core filter + fp32 re-rank must return the fp32 answer
+    (same ids except inside near-ties, distances to 1e-5 relative), for IP and L2, incl. partial query / base tiles."""
+    rng = np.random.default_rng(11)
+    nb, nq, dim, K = 300_017, 3001, 200, 100
+    cent = rng.standard_normal((64, dim)).astype(np.float32)
+    base = (cent[rng.integers(0, 64, nb)] + 0.7 * rng.standard_normal((nb, dim))).astype(np.float32)
+    q = (cent[rng.integers(0, 64, nq)] + 0.9 * rng.standard_normal((nq, dim))).astype(np.float32)
+    for metric in ("ip", "l2"):
+        monkeypatch.setenv("RG_KNN_MODE", "simt")
+        si, sd = rg.knn(base, q, K, metric)
+        monkeypatch.setenv("RG_KNN_MODE", "tc")
+        ti, td = rg.knn(base, q, K, metric)
+        np.testing.assert_allclose(td, sd, rtol=2e-5, atol=1e-4)
+        same = (ti == si)
+        assert same.mean() > 0.999, same.mean()
+        # wherever ids differ the two distances must be a near-tie
+        bad = ~same
+        assert np.all(np.abs(td[bad] - sd[bad]) <= 1e-4 + 2e-5 * np.abs(sd[bad]))
+        assert (np.diff(td, axis=1) >= 0).all()
