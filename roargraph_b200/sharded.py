@@ -25,11 +25,13 @@ def gather_topk(local_dists, local_ids, group=None):
     import torch.distributed as dist
 
     G = dist.get_world_size(group)
-    out_d = torch.empty((G,) + tuple(local_dists.shape), dtype=local_dists.dtype, device=local_dists.device)
-    out_i = torch.empty((G,) + tuple(local_ids.shape), dtype=local_ids.dtype, device=local_ids.device)
+    nq, k = local_dists.shape
+    # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [G][nq][k]
+    out_d = torch.empty((G * nq, k), dtype=local_dists.dtype, device=local_dists.device)
+    out_i = torch.empty((G * nq, k), dtype=local_ids.dtype, device=local_ids.device)
     dist.all_gather_into_tensor(out_d, local_dists.contiguous(), group=group)
     dist.all_gather_into_tensor(out_i, local_ids.contiguous(), group=group)
-    return out_d, out_i
+    return out_d.view(G, nq, k), out_i.view(G, nq, k)
 
 
 class ShardedRoarIndex:

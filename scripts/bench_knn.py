@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Brute-force kNN throughput (pairs/s) of rg_knn_dev on synthetic t2i-shaped data, tensor-core filter vs SIMT tile.
+usage: bench_knn.py [NB] [NQ] [DIM] [K] [modes]     e.g.  bench_knn.py 10000000 1000000 200 100 tc"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import roargraph_b200 as rg
+from roargraph_b200 import synth
+
+nb = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+nq = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
+dim = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+modes = sys.argv[5].split(",") if len(sys.argv) > 5 else ["tc", "simt"]
+rg.init(0)
+dev = torch.device("cuda", 0)
+base, train, _ = synth.make_torch(nb, nq, 8, dim, dev)
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+ids = torch.empty((nq, K), dtype=torch.int32, device=dev); d = torch.empty((nq, K), dtype=torch.float32, device=dev)
+res = {}
+for mode in modes:
+    os.environ["RG_KNN_MODE"] = mode
+    for metric in ("ip",):
+        rg.knn_dev(base[:4096], train[:256], K, metric, ids[:256], d[:256])  # warm-up (module load, attributes)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rg.knn_dev(base, train, K, metric, ids, d)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res[mode] = ids.clone()
+        tf = 2.0 * nq * nb * dim / dt / 1e12
+        print(json.dumps({"mode": mode, "metric": metric, "nb": nb, "nq": nq, "dim": dim, "K": K, "seconds": dt,
+                          "pairs_per_s": nq * nb / dt, "tflops": tf,
+                          "frac_of_measured_bf16_sustained": tf / peaks["bf16_tflops_sustained"]}), flush=True)
+if len(res) == 2:
+    a, b = res["tc"], res["simt"]
+    print(json.dumps({"ids_equal_fraction": float((a == b).float().mean())}))

@@ -1,0 +1,144 @@
+"""The C++ host mirror (roargraph_b200/host): CLIs keep the reference's flags and error behaviour (CPU part), and on a
+GPU produce the same table / files as the reference's own CLIs compiled unmodified (oracle/_ref)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_cuda
+from roargraph_b200 import formats as F
+
+BIN = os.path.join(ROOT, "roargraph_b200", "host", "bin")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(os.path.join(BIN, "test_search_roargraph")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "roargraph_b200", "host"), "-j", "4"])
+
+
+def run(exe, *args):
+    return subprocess.run([os.path.join(BIN, exe), *map(str, args)], capture_output=True, text=True)
+
+
+def test_help_and_missing_arguments():
+    for exe, flag in (("test_search_roargraph", "--L_pq"), ("test_build_roargraph", "--learn_base_nn_path"),
+                      ("compute_groundtruth", "--dist_fn")):
+        p = run(exe, "--help")
+        assert p.returncode == 0 and flag in p.stdout
+        p = run(exe)
+        assert p.returncode == 255 and "required but missing" in p.stderr  # the reference returns -1 (:114-117)
+    p = run("test_search_roargraph", "--bogus", "1")
+    assert p.returncode == 255 and "unrecognised option" in p.stderr
+
+
+def _write_case(tmp_path, golden):
+    bf, qf, gf, idx = (str(tmp_path / n) for n in ("base.fbin", "query.fbin", "gt.bin", "index.rg"))
+    F.write_fbin(bf, golden.base_raw)
+    F.write_fbin(qf, golden.test_raw)
+    gt_d = golden.z["gt_dists"]
+    F.write_truthset(gf, golden.z["gt_ids"], gt_d)
+    golden.z["index_words"].tofile(idx)
+    return bf, qf, gf, idx
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful on a machine without a GPU")
+def test_search_cli_fails_loudly_without_gpu(tmp_path):
+    from conftest import GoldenCase
+    g = GoldenCase("ip_d40")
+    bf, qf, gf, idx = _write_case(tmp_path, g)
+    p = run("test_search_roargraph", "--data_type", "float", "--dist", "ip", "--base_data_path", bf, "--query_path", qf,
+            "--gt_path", gf, "--projection_index_save_path", idx, "--L_pq", 10, 20, "--k", 10)
+    assert p.returncode == 255 and "no CUDA device" in p.stderr
+    p = run("test_search_roargraph", "--data_type", "float", "--dist", "ip", "--base_data_path", bf, "--query_path", qf,
+            "--gt_path", gf, "--projection_index_save_path", str(tmp_path / "missing.rg"), "--L_pq", 10, "--k", 10)
+    assert p.returncode == 255 and "projection index file does not exist" in p.stdout
+
+
+def _table(stdout):
+    rows = {}
+    on = False
+    for ln in stdout.splitlines():
+        if ln.startswith("L_pq"):
+            on = True
+            continue
+        f = ln.split()
+        if on and len(f) >= 6 and f[0].isdigit():
+            rows[int(f[0])] = [float(x) for x in f[1:6]]  # qps, avg_cmps, mean_latency, recall, avg_hops
+    return rows
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_test_search_roargraph")), reason="oracle/_ref not available")
+def test_search_cli_table_matches_reference_cli(tmp_path, golden):
+    bf, qf, gf, idx = _write_case(tmp_path, golden)
+    Ls = [10, 20, 50, 100]
+    args = ["--data_type", "float", "--dist", golden.metric, "--base_data_path", bf, "--query_path", qf, "--gt_path", gf,
+            "--projection_index_save_path", idx, "--L_pq", *map(str, Ls), "--k", "10", "-T", "2"]
+    csv = str(tmp_path / "eval.csv")
+    ours = subprocess.run([os.path.join(BIN, "test_search_roargraph"), *args, "--evaluation_save_path", csv],
+                          capture_output=True, text=True)
+    assert ours.returncode == 0, ours.stderr + ours.stdout
+    ref = subprocess.run([os.path.join(REF, "ref_test_search_roargraph"), *args], capture_output=True, text=True)
+    assert ref.returncode == 0, ref.stderr
+    to, tr = _table(ours.stdout), _table(ref.stdout)
+    assert sorted(to) == sorted(tr) == Ls
+    for L in Ls:
+        # avg_cmps, recall, avg_hops are deterministic functions of the results: equal to print precision.
+        # (cosine: host normalisation agrees with the reference's vectorised loop to rounding only, so allow 1e-3)
+        tol = 1e-3 if golden.metric == "cosine" else 1e-6
+        assert to[L][1] == pytest.approx(tr[L][1], rel=tol), (L, to[L], tr[L])
+        assert to[L][3] == pytest.approx(tr[L][3], abs=tol + 1e-6)
+        assert to[L][4] == pytest.approx(tr[L][4], rel=tol)
+    lines = open(csv).read().strip().splitlines()
+    assert len(lines) == len(Ls) and all(len(l.split(",")) == 7 for l in lines)  # reference's 6 columns + GB/s
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_compute_groundtruth")), reason="oracle/_ref not available")
+@pytest.mark.parametrize("dist_fn", ["mips", "l2", "cosine"])
+def test_compute_groundtruth_cli_matches_reference_cli(tmp_path, dist_fn):
+    from test_oracle_golden import check_knn
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((6000, 96)).astype(np.float32)
+    q = rng.standard_normal((200, 96)).astype(np.float32)
+    bf, qf = str(tmp_path / "b.fbin"), str(tmp_path / "q.fbin")
+    F.write_fbin(bf, base)
+    F.write_fbin(qf, q)
+    outs = []
+    for exe, name in ((os.path.join(BIN, "compute_groundtruth"), "ours.gt"), (os.path.join(REF, "ref_compute_groundtruth"), "ref.gt")):
+        gt = str(tmp_path / name)
+        p = subprocess.run([exe, "--data_type", "float", "--dist_fn", dist_fn, "--base_file", bf, "--query_file", qf,
+                            "--gt_file", gt, "--K", "50"], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout + p.stderr
+        outs.append(F.read_truthset(gt))
+    (oi, od), (ri, rd) = outs
+    assert oi.shape == ri.shape == (200, 50) and od is not None
+    sign = -1.0 if dist_fn == "mips" else 1.0  # stored as +IP for mips: compare as ascending internal distances
+    check_knn(oi, sign * od, ri, sign * rd)
+
+
+@pytest.mark.gpu
+def test_build_cli_then_search_cli(tmp_path, golden):
+    import roargraph_b200 as rg
+    bf, qf, gf, _ = _write_case(tmp_path, golden)
+    tf, kf, idx = str(tmp_path / "train.fbin"), str(tmp_path / "train.gt"), str(tmp_path / "built.rg")
+    train = golden.z["train"] if "train" in golden.z else golden.test_raw
+    F.write_fbin(tf, train)
+    kmetric = "l2" if golden.metric == "l2" else ("cosine" if golden.metric == "cosine" else "ip")
+    ids, d = rg.knn(golden.base_raw, train, 50, kmetric)
+    F.write_truthset(kf, ids.astype(np.uint32), d)
+    p = run("test_build_roargraph", "--data_type", "float", "--dist", golden.metric, "--base_data_path", bf,
+            "--sampled_query_data_path", tf, "--projection_index_save_path", idx, "--learn_base_nn_path", kf, "--M_sq", 50,
+            "--M_pjbp", 16, "--L_pjpq", 64, "-T", 2)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Projection degree max" in p.stdout
+    ep, row_off, nbrs = F.read_projection_index(idx)
+    assert len(row_off) == golden.base.shape[0] + 1 and np.diff(row_off.astype(np.int64)).max() <= 32
+    p = run("test_search_roargraph", "--data_type", "float", "--dist", golden.metric, "--base_data_path", bf, "--query_path",
+            qf, "--gt_path", gf, "--projection_index_save_path", idx, "--L_pq", 100, "--k", 10)
+    assert p.returncode == 0, p.stdout + p.stderr
+    t = _table(p.stdout)
+    assert t[100][3] > 0.9  # recall@10 on the CLI-built index
