@@ -143,16 +143,32 @@ __global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t 
         __syncthreads();
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         const float qq = rr.metric_l2 ? rr.qn[q] : 0.f;
-        for (uint32_t i = warp; i < n; i += nwarps) {
-            const uint32_t b = (uint32_t)cand[q * cap + i];
-            const float *br = rr.base + (uint64_t)b * rr.dim;
-            float acc = 0.f;
-            for (uint32_t j = lane; j < rr.dim; j += 32) acc = fmaf(sq[j], __ldg(br + j), acc);
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                const float d = rr.metric_l2 ? (-2.0f * acc + rr.bn[b]) + qq : -acc;
-                cand[q * cap + i] = ((unsigned long long)f2ord(d) << 32) | b;
+        // four candidates per warp pass: their row loads are independent, so the DRAM latencies overlap
+        for (uint32_t i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
+            uint32_t b[4];
+            const float *br[4];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                b[t] = (uint32_t)cand[q * cap + min(i0 + t, n - 1)];
+                br[t] = rr.base + (uint64_t)b[t] * rr.dim;
             }
+            for (uint32_t j = lane; j < rr.dim; j += 32) {
+                const float qv = sq[j];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] = fmaf(qv, __ldg(br[t] + j), acc[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+            __syncwarp();
+            if (lane < 4 && i0 + lane < n) {
+                const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+                const uint32_t bb = lane == 0 ? b[0] : lane == 1 ? b[1] : lane == 2 ? b[2] : b[3];
+                const float d = rr.metric_l2 ? (-2.0f * a + rr.bn[bb]) + qq : -a;
+                cand[q * cap + i0 + lane] = ((unsigned long long)f2ord(d) << 32) | bb;
+            }
+            __syncwarp();
         }
         __syncthreads();
     }
