@@ -281,7 +281,9 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
 
     const bool tc = use_tensor_cores(dim);
     const uint32_t cap = std::max<uint32_t>(2048u, 4u * K);
-    const uint64_t chunk0 = tc ? (cap / 256u) * 256u : cap;  // tensor-core tiles are 256 base rows
+    // first chunk: everything survives (tau = inf), so keep it small on the tensor-core path (one 256-row tile);
+    // chunks then double, which keeps the expected survivors per chunk near K
+    const uint64_t chunk0 = tc ? 256u : cap;
     uint32_t sort_n = 1;
     while (sort_n < cap + K) sort_n <<= 1;
     // query batches so that the candidate lists stay within ~2 GiB
@@ -356,7 +358,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
             const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
             knn_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, s>>>(top, nqb * K, tau, cnt, nqb);
             RG_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), s));
-            uint64_t lo = 0, csize = chunk0;
+            uint64_t lo = 0, csize = attempt == 0 ? chunk0 : (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap);
             while (lo < nb) {
                 const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
                 if (tc) {

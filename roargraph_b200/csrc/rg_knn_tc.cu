@@ -17,19 +17,19 @@
 #include <cuda_bf16.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "rg_internal.h"
 
 namespace rg {
 namespace {
 
-constexpr int kBlockM = 128;   // queries per CTA
-constexpr int kBlockN = 256;   // base rows per tile
+constexpr int kBlockM = 128;   // queries per query tile (UMMA M)
+constexpr int kAccCols = 256;  // TMEM columns per accumulator set; two sets = all 512 columns
 constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr uint32_t kABytesPerKb = kBlockM * kBlockK * 2;  // 16 KB
-constexpr uint32_t kBBytesPerKb = kBlockN * kBlockK * 2;  // 32 KB
 constexpr int kMaxKb = 8;      // dim <= 512
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,7 +75,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns of the warp's TMEM lane quadrant
+// 32 lanes x 32 consecutive fp32 columns of the warp's TMEM lane quadrant (asynchronous: pair with tc_ld_wait)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -87,8 +87,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); version 1 (sm_100);
 // layout type 2 = SWIZZLE_128B.  The tile base must be 1024-byte aligned; a k-step of 16 bf16 advances the start by 32 B.
@@ -101,8 +101,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
 
 struct TcParams {
     uint64_t nq;            // queries in this batch (rows of the A tensor map)
@@ -110,9 +112,10 @@ struct TcParams {
     uint32_t num_kb;        // 64-column k-blocks
     uint32_t ksteps_last;   // k-steps of 16 in the last k-block
     uint32_t stages;        // ring depth (k-blocks of B)
-    uint32_t tile_lo, tile_hi;  // base tiles [tile_lo, tile_hi) of this chunk
+    uint32_t tile_lo, tile_hi;  // base tiles [tile_lo, tile_hi) of this chunk, in units of the kernel's BLOCK_N
     uint32_t tiles_per_cta;
     int metric_l2;
+    int atomic_append;      // several CTAs share a query (base range split over blockIdx.y)
     const float *tau;       // running K-th best internal distance per query
     const float *qn;        // ||q||^2 (exact fp32)
     const float *bn;        // ||b||^2
@@ -123,15 +126,23 @@ struct TcParams {
     uint32_t *overflow;
 };
 
+// NQT = query tiles per CTA.  NQT == 2 (dim <= 256): 256 queries share every base tile, which halves the L2 -> SM operand
+// traffic per flop — the limiter of this small-K GEMM (profiles/r1_knn_tc_2M_ncu_full.txt); base tiles are then 128 rows
+// so that {2 query tiles} x {2 tiles in flight} x 128 columns fill the 512 TMEM columns.  NQT == 1: one query tile, 256-row
+// base tiles.
+template <int NQT>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                      const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    constexpr int BLOCK_N = kAccCols / NQT;
+    constexpr uint32_t kBBytesPerKb = BLOCK_N * kBlockK * 2;
+    constexpr uint32_t kIdesc = make_idesc(BLOCK_N);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [A: num_kb x 16 KB][B ring: stages x 32 KB][bn: 2 x 256 floats][barriers][tmem ptr]
+    // carve: [A: NQT x num_kb x 16 KB][B ring: stages x kBBytesPerKb][bn: 2 x BLOCK_N floats][barriers][tmem ptr]
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
-    uint8_t *sB = sA + (size_t)p.num_kb * kABytesPerKb;
+    uint8_t *sB = sA + (size_t)NQT * p.num_kb * kABytesPerKb;
     float *s_bn = reinterpret_cast<float *>(sB + (size_t)p.stages * kBBytesPerKb);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_bn + 2 * kBlockN);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_bn + 2 * BLOCK_N);
     // bars: [0] a_full, [1..1+S) full, [1+S..1+2S) empty, then tmem_full[2], tmem_empty[2]
     const uint32_t S = p.stages;
     const uint32_t bar_a = smem_u32(bars);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 1 + 2 * S + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t q0 = (uint64_t)blockIdx.x * kBlockM;
+    const uint64_t q0 = (uint64_t)blockIdx.x * (kBlockM * NQT);
     const uint32_t t_begin = p.tile_lo + blockIdx.y * p.tiles_per_cta;
     const uint32_t t_end = min(p.tile_hi, t_begin + p.tiles_per_cta);
     const uint32_t n_tiles = t_end > t_begin ? t_end - t_begin : 0;
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators); this warp also frees them
+    if (warp == 1) {  // TMEM: all 512 columns (two accumulator sets); this warp also frees them
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -171,17 +182,19 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0 && n_tiles) {
-            // query tile, resident
-            mbar_expect_tx(bar_a, p.num_kb * kABytesPerKb);
-            for (uint32_t kb = 0; kb < p.num_kb; ++kb)
-                tma_load_2d(smem_u32(sA + (size_t)kb * kABytesPerKb), &map_q, bar_a, (int)(kb * kBlockK), (int)q0);
+            // query tiles, resident for the CTA's lifetime
+            mbar_expect_tx(bar_a, NQT * p.num_kb * kABytesPerKb);
+            for (int j = 0; j < NQT; ++j)
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb)
+                    tma_load_2d(smem_u32(sA + ((size_t)j * p.num_kb + kb) * kABytesPerKb), &map_q, bar_a, (int)(kb * kBlockK),
+                                (int)(q0 + (uint64_t)j * kBlockM));
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     mbar_expect_tx(bar_full + 8 * stage, kBBytesPerKb);
                     tma_load_2d(smem_u32(sB + (size_t)stage * kBBytesPerKb), &map_b, bar_full + 8 * stage, (int)(kb * kBlockK),
-                                (int)(t * kBlockN));
+                                (int)(t * BLOCK_N));
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
@@ -196,93 +209,115 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
             uint32_t stage = 0, phase = 0;
             for (uint32_t i = 0; i < n_tiles; ++i) {
                 const uint32_t buf = i & 1;
-                mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * kBlockN;
+                const uint32_t d_tmem = tmem_base + buf * kAccCols;
                 for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + (size_t)kb * kABytesPerKb));
                     const uint64_t b_desc = umma_desc_sw128(smem_u32(sB + (size_t)stage * kBBytesPerKb));
                     const uint32_t nk = (kb == p.num_kb - 1) ? p.ksteps_last : (uint32_t)(kBlockK / kUmmaK);
-                    for (uint32_t k = 0; k < nk; ++k)
-                        tc_mma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int j = 0; j < NQT; ++j) {
+                        const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + ((size_t)j * p.num_kb + kb) * kABytesPerKb));
+                        for (uint32_t k = 0; k < nk; ++k)
+                            tc_mma_bf16(d_tmem + j * BLOCK_N, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc,
+                                        (kb | k) != 0 ? 1u : 0u);
+                    }
                     tc_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs have read it
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(bar_tfull + 8 * buf);  // accumulator complete
+                tc_commit(bar_tfull + 8 * buf);  // accumulator set complete
             }
         }
     } else {
-        // epilogue: TMEM lane quadrant = warp id % 4; this thread owns query row `row`
+        // epilogue: TMEM lane quadrant = warp id % 4; this thread owns row `row` of every query tile of the CTA
         const uint32_t quad = (uint32_t)warp & 3u;
         const uint32_t row = quad * 32 + lane;
-        const uint64_t q = q0 + row;
-        const bool q_ok = q < p.nq;
         const int epi_tid = threadIdx.x - 64;  // 0..127
         // keep a score iff its exact distance can still be below tau:  |dot_bf16 - dot| <= E
-        float theta = INFINITY;  // rows past the batch never pass
-        if (q_ok) {
-            const float t = p.tau[q];
-            const float qq = p.qn[q];
-            const float E = 1.01f * 0.0078125f * sqrtf(qq) * p.bmax;  // (2u + u^2) ||q|| ||b||, u = 2^-8, with slack
-            if (p.metric_l2) theta = (qq - t) - 2.f * E;                 // keep iff 2 dot - ||b||^2 > theta
-            else theta = (-t) - E;                                      // keep iff dot > theta
-            if (t == INFINITY) theta = -INFINITY;
+        float theta[NQT];
+        uint32_t cnt[NQT];
+        uint64_t qrow[NQT];
+#pragma unroll
+        for (int j = 0; j < NQT; ++j) {
+            qrow[j] = q0 + (uint64_t)j * kBlockM + row;
+            cnt[j] = 0;
+            theta[j] = INFINITY;  // rows past the batch never pass
+            if (qrow[j] < p.nq) {
+                const float t = p.tau[qrow[j]];
+                const float qq = p.qn[qrow[j]];
+                const float E = 1.01f * 0.0078125f * sqrtf(qq) * p.bmax;  // (2u + u^2) ||q|| ||b||, u = 2^-8, with slack
+                if (p.metric_l2) theta[j] = (qq - t) - 2.f * E;            // keep iff 2 dot - ||b||^2 > theta
+                else theta[j] = (-t) - E;                                 // keep iff dot > theta
+                if (t == INFINITY) theta[j] = -INFINITY;
+            }
         }
-        unsigned long long *my_cand = p.cand + q * p.cap;
         for (uint32_t i = 0; i < n_tiles; ++i) {
             const uint32_t buf = i & 1;
             const uint32_t tile = t_begin + i;
-            const uint64_t col0 = (uint64_t)tile * kBlockN;
+            const uint64_t col0 = (uint64_t)tile * BLOCK_N;
             if (p.metric_l2) {
-                // ||b||^2 of this tile's 256 rows -> shared (double-buffered with the accumulators)
-                for (int j = epi_tid; j < kBlockN; j += 128) {
+                // ||b||^2 of this tile's rows -> shared (double-buffered with the accumulator sets)
+                for (int j = epi_tid; j < BLOCK_N; j += 128) {
                     const uint64_t b = col0 + j;
-                    s_bn[buf * kBlockN + j] = b < p.nb ? __ldg(p.bn + b) : 0.f;
+                    s_bn[buf * BLOCK_N + j] = b < p.nb ? __ldg(p.bn + b) : 0.f;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kBlockN;
-#pragma unroll 1
-            for (uint32_t c = 0; c < kBlockN / 32; ++c) {
-                uint32_t r[32];
-                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after a divergent survivor scan
-                tc_ld32(taddr + c * 32, r);
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kAccCols;
+            uint32_t r[2][32];
+            __syncwarp();
+            tc_ld32(taddr, r[0]);
+#pragma unroll
+            for (int cc = 0; cc < kAccCols / 32; ++cc) {
+                tc_ld_wait();
+                if (cc + 1 < kAccCols / 32) tc_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // overlaps the scan below
+                const int j = (cc * 32) / BLOCK_N;        // query tile of this 32-column group
+                const int cin = (cc * 32) % BLOCK_N;      // first column within the base tile
+                const uint32_t(&rr)[32] = r[cc & 1];
                 float v[32];
                 if (p.metric_l2) {
-                    const float *bn = s_bn + buf * kBlockN + c * 32;
+                    const float *bn = s_bn + buf * BLOCK_N + cin;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaf(2.f, __uint_as_float(r[j]), -bn[j]);
+                    for (int e = 0; e < 32; ++e) v[e] = fmaf(2.f, __uint_as_float(rr[e]), -bn[e]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rr[e]);
                 }
                 float m = v[0];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-                if (m > theta) {  // rare once tau has tightened
+                for (int e = 1; e < 32; ++e) m = fmaxf(m, v[e]);
+                if (m > theta[j]) {  // rare once tau has tightened
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (v[j] > theta) {
-                            const uint64_t b = col0 + c * 32 + j;
-                            if (b < p.nb) {
-                                const uint32_t slot = atomicAdd(p.cand_cnt + q, 1u);
-                                if (slot < p.cap) my_cand[slot] = (unsigned long long)(uint32_t)b;
-                                else *p.overflow = 1u;
-                            }
+                    for (int e = 0; e < 32; ++e) mask |= (v[e] > theta[j] ? 1u : 0u) << e;
+                    while (mask) {
+                        const int e = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint64_t b = col0 + cin + e;
+                        if (b < p.nb) {
+                            const uint32_t slot = p.atomic_append ? atomicAdd(p.cand_cnt + qrow[j], 1u) : cnt[j]++;
+                            if (slot < p.cap) p.cand[qrow[j] * p.cap + slot] = (unsigned long long)(uint32_t)b;
+                            else *p.overflow = 1u;
                         }
                     }
                 }
+                __syncwarp();  // tcgen05.ld / wait are .sync.aligned: reconverge after a divergent survivor scan
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        if (!p.atomic_append) {
+#pragma unroll
+            for (int j = 0; j < NQT; ++j)
+                if (qrow[j] < p.nq && cnt[j]) p.cand_cnt[qrow[j]] = cnt[j];
         }
     }
     tc_fence_before();
@@ -373,34 +408,48 @@ int knn_tc_max_norm(const float *sq, uint64_t n, float *d_out, cudaStream_t s) {
 }
 
 // One chunk [row_lo, row_hi) of the base (both multiples of 256, or row_hi == nb) against one query batch.
+template <int NQT>
+static int launch_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t kp, uint64_t row_lo,
+                         uint64_t row_hi, TcParams p, int sm_count, cudaStream_t s) {
+    constexpr int BLOCK_N = kAccCols / NQT;
+    constexpr uint32_t kBBytesPerKb = BLOCK_N * kBlockK * 2;
+    CUtensorMap map_q, map_b;
+    int rc = make_map(&map_q, q_bf16, nq, kp, kBlockM);
+    if (rc != RG_OK) return rc;
+    rc = make_map(&map_b, b_bf16, nb, kp, BLOCK_N);
+    if (rc != RG_OK) return rc;
+    const size_t fixed = (size_t)NQT * p.num_kb * kABytesPerKb + 2 * BLOCK_N * 4 + 512 + 1024;
+    const size_t budget = 227 * 1024;
+    if (fixed + 2 * kBBytesPerKb > budget) { set_error("rg_knn: dimension too large for the tensor-core path"); return RG_EINVAL; }
+    uint32_t stages = (uint32_t)((budget - fixed) / kBBytesPerKb);
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    p.tile_lo = (uint32_t)(row_lo / BLOCK_N);
+    p.tile_hi = (uint32_t)((row_hi + BLOCK_N - 1) / BLOCK_N);
+    const uint32_t tiles = p.tile_hi - p.tile_lo;
+    const uint32_t q_tiles = (uint32_t)((nq + kBlockM * NQT - 1) / (kBlockM * NQT));
+    uint32_t splits = 1;
+    if (q_tiles < 2u * (uint32_t)sm_count) splits = std::min<uint32_t>(tiles, (2u * (uint32_t)sm_count + q_tiles - 1) / q_tiles);
+    p.tiles_per_cta = (tiles + splits - 1) / splits;
+    splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    p.atomic_append = splits > 1 ? 1 : 0;
+    const size_t smem = fixed + (size_t)stages * kBBytesPerKb;
+    RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(q_tiles, splits);
+    knn_tc_filter_kernel<NQT><<<grid, kThreads, smem, s>>>(map_q, map_b, p);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
 int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
                   int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
                   uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s) {
     const uint32_t kp = knn_tc_pitch(dim);
-    CUtensorMap map_q, map_b;
-    int rc = make_map(&map_q, q_bf16, nq, kp, kBlockM);
-    if (rc != RG_OK) return rc;
-    rc = make_map(&map_b, b_bf16, nb, kp, kBlockN);
-    if (rc != RG_OK) return rc;
     TcParams p{};
     p.nq = nq;
     p.nb = nb;
     p.num_kb = (kp + kBlockK - 1) / kBlockK;
     p.ksteps_last = ((kp - (p.num_kb - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
-    const size_t fixed = (size_t)p.num_kb * kABytesPerKb + 2 * kBlockN * 4 + 512 + 1024;
-    const size_t budget = 227 * 1024;
-    uint32_t stages = (uint32_t)((budget - fixed) / kBBytesPerKb);
-    if (stages > 6) stages = 6;
-    if (stages < 2) { set_error("rg_knn: dimension too large for the tensor-core path"); return RG_EINVAL; }
-    p.stages = stages;
-    p.tile_lo = (uint32_t)(row_lo / kBlockN);
-    p.tile_hi = (uint32_t)((row_hi + kBlockN - 1) / kBlockN);
-    const uint32_t tiles = p.tile_hi - p.tile_lo;
-    const uint32_t q_tiles = (uint32_t)((nq + kBlockM - 1) / kBlockM);
-    uint32_t splits = 1;
-    if (q_tiles < 2u * (uint32_t)sm_count) splits = std::min<uint32_t>(tiles, (2u * (uint32_t)sm_count + q_tiles - 1) / q_tiles);
-    p.tiles_per_cta = (tiles + splits - 1) / splits;
-    splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     p.metric_l2 = metric_l2;
     p.tau = tau;
     p.qn = qn;
@@ -410,12 +459,10 @@ int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t 
     p.cand_cnt = cand_cnt;
     p.cap = cap;
     p.overflow = overflow;
-    const size_t smem = fixed + (size_t)stages * kBBytesPerKb;
-    RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(q_tiles, splits);
-    knn_tc_filter_kernel<<<grid, kThreads, smem, s>>>(map_q, map_b, p);
-    RG_CUDA(cudaGetLastError());
-    return RG_OK;
+    const char *force = getenv("RG_KNN_QTILES");
+    const bool two = force ? force[0] == '2' : (p.num_kb <= 4 && nq > (uint64_t)kBlockM);
+    if (two && p.num_kb <= 4) return launch_filter<2>(q_bf16, nq, b_bf16, nb, kp, row_lo, row_hi, p, sm_count, s);
+    return launch_filter<1>(q_bf16, nq, b_bf16, nb, kp, row_lo, row_hi, p, sm_count, s);
 }
 
 }  // namespace rg

@@ -37,9 +37,11 @@ def test_help_and_missing_arguments():
 def _write_case(tmp_path, golden):
     bf, qf, gf, idx = (str(tmp_path / n) for n in ("base.fbin", "query.fbin", "gt.bin", "index.rg"))
     F.write_fbin(bf, golden.base_raw)
-    F.write_fbin(qf, golden.test_raw)
-    gt_d = golden.z["gt_dists"]
-    F.write_truthset(gf, golden.z["gt_ids"], gt_d)
+    # the reference CLI warms up on queries 0..99 unconditionally (tests/test_search_roargraph.cpp:198-200) and reads
+    # out of bounds with fewer: repeat the fixture's queries up to >= 100 rows
+    reps = -(-100 // golden.test_raw.shape[0])
+    F.write_fbin(qf, np.tile(golden.test_raw, (reps, 1)))
+    F.write_truthset(gf, np.tile(golden.z["gt_ids"], (reps, 1)), np.tile(golden.z["gt_dists"], (reps, 1)))
     golden.z["index_words"].tofile(idx)
     return bf, qf, gf, idx
 
