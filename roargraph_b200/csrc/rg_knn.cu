@@ -287,7 +287,12 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     uint32_t sort_n = 1;
     while (sort_n < cap + K) sort_n <<= 1;
     // query batches so that the candidate lists stay within ~2 GiB
-    const uint64_t qb_max = std::max<uint64_t>(TQ, ((2ull << 30) / (cap * 8ull)) / TQ * TQ);
+    uint64_t qb_max = std::max<uint64_t>(TQ, ((2ull << 30) / (cap * 8ull)) / TQ * TQ);
+    if (tc) {  // whole waves of the tensor-core filter: one CTA = 256 queries, one CTA per SM
+        const uint64_t wave = (uint64_t)sm_count() * 256u;
+        const uint64_t fit = ((2600ull << 20) / (cap * 8ull)) / wave * wave;
+        if (fit) qb_max = fit;
+    }
 
     Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf, s_b16, s_q16, s_max;
     float *bn = nullptr, *qn = nullptr;

@@ -28,7 +28,7 @@ constexpr int kBlockM = 128;   // queries per query tile (UMMA M)
 constexpr int kAccCols = 256;  // TMEM columns per accumulator set; two sets = all 512 columns
 constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr uint32_t kABytesPerKb = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxKb = 8;      // dim <= 512
 
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * b, 8);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -234,56 +234,54 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
             }
         }
     } else {
-        // epilogue: TMEM lane quadrant = warp id % 4; this thread owns row `row` of every query tile of the CTA
+        // epilogue, 8 warps: TMEM lane quadrant = warp id % 4 (hardware rule), column half = (warp - 2) / 4.
+        // A thread owns one accumulator row and 128 of the 256 columns of a set: with NQT == 2 that is exactly one query
+        // (tile `half`, row `row`), whose threshold and candidate count live in registers.
         const uint32_t quad = (uint32_t)warp & 3u;
+        const uint32_t half = (uint32_t)(warp - 2) >> 2;
         const uint32_t row = quad * 32 + lane;
-        const int epi_tid = threadIdx.x - 64;  // 0..127
+        const int epi_tid = threadIdx.x - 64;  // 0..255
+        const uint32_t jq = (half * 128u) / BLOCK_N;       // query tile of this thread's columns
+        const uint32_t cbase = (half * 128u) % BLOCK_N;    // first base-tile column of this thread's columns
+        const uint64_t qrow = q0 + (uint64_t)jq * kBlockM + row;
+        uint32_t cnt = 0;
         // keep a score iff its exact distance can still be below tau:  |dot_bf16 - dot| <= E
-        float theta[NQT];
-        uint32_t cnt[NQT];
-        uint64_t qrow[NQT];
-#pragma unroll
-        for (int j = 0; j < NQT; ++j) {
-            qrow[j] = q0 + (uint64_t)j * kBlockM + row;
-            cnt[j] = 0;
-            theta[j] = INFINITY;  // rows past the batch never pass
-            if (qrow[j] < p.nq) {
-                const float t = p.tau[qrow[j]];
-                const float qq = p.qn[qrow[j]];
-                const float E = 1.01f * 0.0078125f * sqrtf(qq) * p.bmax;  // (2u + u^2) ||q|| ||b||, u = 2^-8, with slack
-                if (p.metric_l2) theta[j] = (qq - t) - 2.f * E;            // keep iff 2 dot - ||b||^2 > theta
-                else theta[j] = (-t) - E;                                 // keep iff dot > theta
-                if (t == INFINITY) theta[j] = -INFINITY;
-            }
+        float theta = INFINITY;  // rows past the batch never pass
+        if (qrow < p.nq) {
+            const float t = p.tau[qrow];
+            const float qq = p.qn[qrow];
+            const float E = 1.01f * 0.0078125f * sqrtf(qq) * p.bmax;  // (2u + u^2) ||q|| ||b||, u = 2^-8, with slack
+            if (p.metric_l2) theta = (qq - t) - 2.f * E;               // keep iff 2 dot - ||b||^2 > theta
+            else theta = (-t) - E;                                    // keep iff dot > theta
+            if (t == INFINITY) theta = -INFINITY;
         }
+        const bool atomic_append = p.atomic_append || NQT == 1;  // NQT == 1: the two column halves share the query
         for (uint32_t i = 0; i < n_tiles; ++i) {
             const uint32_t buf = i & 1;
             const uint32_t tile = t_begin + i;
-            const uint64_t col0 = (uint64_t)tile * BLOCK_N;
+            const uint64_t col0 = (uint64_t)tile * BLOCK_N + cbase;
             if (p.metric_l2) {
                 // ||b||^2 of this tile's rows -> shared (double-buffered with the accumulator sets)
-                for (int j = epi_tid; j < BLOCK_N; j += 128) {
-                    const uint64_t b = col0 + j;
+                for (int j = epi_tid; j < BLOCK_N; j += 256) {
+                    const uint64_t b = (uint64_t)tile * BLOCK_N + j;
                     s_bn[buf * BLOCK_N + j] = b < p.nb ? __ldg(p.bn + b) : 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kAccCols;
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kAccCols + half * 128u;
             uint32_t r[2][32];
             __syncwarp();
             tc_ld32(taddr, r[0]);
 #pragma unroll
-            for (int cc = 0; cc < kAccCols / 32; ++cc) {
+            for (int cc = 0; cc < 4; ++cc) {
                 tc_ld_wait();
-                if (cc + 1 < kAccCols / 32) tc_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // overlaps the scan below
-                const int j = (cc * 32) / BLOCK_N;        // query tile of this 32-column group
-                const int cin = (cc * 32) % BLOCK_N;      // first column within the base tile
+                if (cc + 1 < 4) tc_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // overlaps the scan below
                 const uint32_t(&rr)[32] = r[cc & 1];
                 float v[32];
                 if (p.metric_l2) {
-                    const float *bn = s_bn + buf * BLOCK_N + cin;
+                    const float *bn = s_bn + buf * BLOCK_N + cbase + cc * 32;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = fmaf(2.f, __uint_as_float(rr[e]), -bn[e]);
                 } else {
@@ -293,17 +291,17 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
                 float m = v[0];
 #pragma unroll
                 for (int e = 1; e < 32; ++e) m = fmaxf(m, v[e]);
-                if (m > theta[j]) {  // rare once tau has tightened
+                if (m > theta) {  // rare once tau has tightened
                     uint32_t mask = 0;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) mask |= (v[e] > theta[j] ? 1u : 0u) << e;
+                    for (int e = 0; e < 32; ++e) mask |= (v[e] > theta ? 1u : 0u) << e;
                     while (mask) {
                         const int e = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const uint64_t b = col0 + cin + e;
+                        const uint64_t b = col0 + cc * 32 + e;
                         if (b < p.nb) {
-                            const uint32_t slot = p.atomic_append ? atomicAdd(p.cand_cnt + qrow[j], 1u) : cnt[j]++;
-                            if (slot < p.cap) p.cand[qrow[j] * p.cap + slot] = (unsigned long long)(uint32_t)b;
+                            const uint32_t slot = atomic_append ? atomicAdd(p.cand_cnt + qrow, 1u) : cnt++;
+                            if (slot < p.cap) p.cand[qrow * p.cap + slot] = (unsigned long long)(uint32_t)b;
                             else *p.overflow = 1u;
                         }
                     }
@@ -314,11 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        if (!p.atomic_append) {
-#pragma unroll
-            for (int j = 0; j < NQT; ++j)
-                if (qrow[j] < p.nq && cnt[j]) p.cand_cnt[qrow[j]] = cnt[j];
-        }
+        if (!atomic_append && qrow < p.nq && cnt) p.cand_cnt[qrow] = cnt;
     }
     tc_fence_before();
     __syncthreads();
