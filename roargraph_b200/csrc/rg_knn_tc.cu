@@ -75,6 +75,34 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, with the descriptors assembled from 32-bit halves inside the asm block (the high word is a launch constant and
+// a k-step only moves the low word), so the issuing loop stays on 32-bit integer math
+__device__ __forceinline__ void tc_mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one lane of a converged warp (the same lane every time for a full mask)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // 32 lanes x 32 consecutive fp32 columns of the warp's TMEM lane quadrant (asynchronous: pair with tc_ld_wait)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -181,20 +209,27 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
-        if (lane == 0 && n_tiles) {
-            // query tiles, resident for the CTA's lifetime
-            mbar_expect_tx(bar_a, NQT * p.num_kb * kABytesPerKb);
-            for (int j = 0; j < NQT; ++j)
-                for (uint32_t kb = 0; kb < p.num_kb; ++kb)
-                    tma_load_2d(smem_u32(sA + ((size_t)j * p.num_kb + kb) * kABytesPerKb), &map_q, bar_a, (int)(kb * kBlockK),
-                                (int)(q0 + (uint64_t)j * kBlockM));
+        // TMA producer: warp-uniform control flow, one elected lane issues
+        if (n_tiles) {
+            if (elect_one()) {
+                // query tiles, resident for the CTA's lifetime
+                mbar_expect_tx(bar_a, NQT * p.num_kb * kABytesPerKb);
+                for (int j = 0; j < NQT; ++j)
+                    for (uint32_t kb = 0; kb < p.num_kb; ++kb)
+                        tma_load_2d(smem_u32(sA + ((size_t)j * p.num_kb + kb) * kABytesPerKb), &map_q, bar_a, (int)(kb * kBlockK),
+                                    (int)(q0 + (uint64_t)j * kBlockM));
+            }
+            __syncwarp();
             uint32_t stage = 0, phase = 0;
+            const uint32_t sB_u32 = smem_u32(sB);
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, kBBytesPerKb);
-                    tma_load_2d(smem_u32(sB + (size_t)stage * kBBytesPerKb), &map_b, bar_full + 8 * stage, (int)(kb * kBlockK),
-                                (int)(t * BLOCK_N));
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * stage, kBBytesPerKb);
+                        tma_load_2d(sB_u32 + stage * kBBytesPerKb, &map_b, bar_full + 8 * stage, (int)(kb * kBlockK), (int)(t * BLOCK_N));
+                    }
+                    __syncwarp();
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
@@ -203,9 +238,15 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && n_tiles) {
+        // MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the descriptor math off the
+        // per-thread path), one elected lane issues the tcgen05.mma / tcgen05.commit instructions
+        if (n_tiles) {
             mbar_wait(bar_a, 0);
             tc_fence_after();
+            const uint64_t d0 = umma_desc_sw128(0);
+            const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)d0 | ((smem_u32(sA) & 0x3ffffu) >> 4);
+            const uint32_t b_lo0 = (uint32_t)d0 | ((smem_u32(sB) & 0x3ffffu) >> 4);
             uint32_t stage = 0, phase = 0;
             for (uint32_t i = 0; i < n_tiles; ++i) {
                 const uint32_t buf = i & 1;
@@ -215,22 +256,28 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
                 for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint64_t b_desc = umma_desc_sw128(smem_u32(sB + (size_t)stage * kBBytesPerKb));
+                    const uint32_t b_lo = b_lo0 + stage * (kBBytesPerKb >> 4);
                     const uint32_t nk = (kb == p.num_kb - 1) ? p.ksteps_last : (uint32_t)(kBlockK / kUmmaK);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < NQT; ++j) {
-                        const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + ((size_t)j * p.num_kb + kb) * kABytesPerKb));
-                        for (uint32_t k = 0; k < nk; ++k)
-                            tc_mma_bf16(d_tmem + j * BLOCK_N, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc,
-                                        (kb | k) != 0 ? 1u : 0u);
+                        for (int j = 0; j < NQT; ++j) {
+                            const uint32_t a_lo = a_lo0 + ((uint32_t)j * p.num_kb + kb) * (kABytesPerKb >> 4);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                                if ((uint32_t)k < nk)
+                                    tc_mma_bf16_lo(d_tmem + j * BLOCK_N, a_lo + 2 * k, b_lo + 2 * k, desc_hi, kIdesc,
+                                                   k == 0 ? (kb != 0 ? 1u : 0u) : 1u);
+                        }
+                        tc_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs have read it
                     }
-                    tc_commit(bar_empty + 8 * stage);  // stage reusable once these MMAs have read it
+                    __syncwarp();
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(bar_tfull + 8 * buf);  // accumulator set complete
+                if (elect_one()) tc_commit(bar_tfull + 8 * buf);  // accumulator set complete
+                __syncwarp();
             }
         }
     } else {
