@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_gemm_filter_kernel(
             if (metric_l2) s = (-2.0f * acc[i][j] + bn[b]) + qq;
             else s = -acc[i][j];
             if (s < t) {
-                const uint32_t slot = atomicAdd(cand_cnt + q, 1u);
+                const uint32_t slot = atomicAdd(cand_cnt + 2 * q, 1u);  // sub-list 0 (see CandList)
                 if (slot < cap) cand[q * cap + slot] = ((unsigned long long)f2ord(s) << 32) | (uint32_t)b;
                 else *overflow = 1u;
             }
@@ -129,60 +129,27 @@ struct Rerank {
     int metric_l2;
 };
 
-__global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t K, unsigned long long *__restrict__ cand,
-                                 uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n,
-                                 const Rerank rr) {
-    extern __shared__ unsigned long long sk[];
-    const uint64_t q = blockIdx.x;
-    uint32_t n = cand_cnt[q];
-    if (n > cap) n = cap;
-    if (n == 0) return;
-    if (rr.base) {
-        float *sq = reinterpret_cast<float *>(sk + sort_n);  // dim floats after the sort buffer
-        for (uint32_t j = threadIdx.x; j < rr.dim; j += blockDim.x) sq[j] = rr.queries[q * rr.dim + j];
-        __syncthreads();
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        const float qq = rr.metric_l2 ? rr.qn[q] : 0.f;
-        // four candidates per warp pass: their row loads are independent, so the DRAM latencies overlap
-        for (uint32_t i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
-            uint32_t b[4];
-            const float *br[4];
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                b[t] = (uint32_t)cand[q * cap + min(i0 + t, n - 1)];
-                br[t] = rr.base + (uint64_t)b[t] * rr.dim;
-            }
-            for (uint32_t j = lane; j < rr.dim; j += 32) {
-                const float qv = sq[j];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) acc[t] = fmaf(qv, __ldg(br[t] + j), acc[t]);
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-            __syncwarp();
-            if (lane < 4 && i0 + lane < n) {
-                const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-                const uint32_t bb = lane == 0 ? b[0] : lane == 1 ? b[1] : lane == 2 ? b[2] : b[3];
-                const float d = rr.metric_l2 ? (-2.0f * a + rr.bn[bb]) + qq : -a;
-                cand[q * cap + i0 + lane] = ((unsigned long long)f2ord(d) << 32) | bb;
-            }
-            __syncwarp();
+// A query's candidate list is `cap` words; the 2-CTA tensor-core filter fills it as two private sub-lists (one per
+// column half of a tile: [0, cap/2) and [cap/2, cap), counters cnt[2q] and cnt[2q+1]) so that no atomic sits on its
+// epilogue path; every other producer appends to sub-list 0 alone, which may then use the whole capacity.
+struct CandList {
+    uint32_t n0, n1, half_cap;
+    __device__ CandList(const uint32_t *cand_cnt, uint64_t q, uint32_t cap) {
+        n0 = cand_cnt[2 * q];
+        n1 = cand_cnt[2 * q + 1];
+        half_cap = cap >> 1;
+        if (n1) {
+            n0 = min(n0, half_cap);
+            n1 = min(n1, half_cap);
+        } else {
+            n0 = min(n0, cap);
         }
-        __syncthreads();
     }
-    // smallest power of two holding n + K
-    uint32_t m = 1;
-    while (m < n + K) m <<= 1;
-    if (m > sort_n) m = sort_n;
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-        unsigned long long v = ~0ull;
-        if (i < n) v = cand[q * cap + i];
-        else if (i < n + K) v = top[q * K + (i - n)];
-        sk[i] = v;
-    }
-    __syncthreads();
+    __device__ uint32_t size() const { return n0 + n1; }
+    __device__ uint32_t slot(uint32_t i) const { return i < n0 ? i : half_cap + (i - n0); }
+};
+
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long *sk, uint32_t m) {
     for (uint32_t size = 2; size <= m; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             for (uint32_t i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
@@ -198,11 +165,184 @@ __global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t 
             __syncthreads();
         }
     }
+}
+
+// General path (any candidate count up to cap): one CTA of 256 threads per query of the work list.
+__device__ void merge_query_big(uint64_t q, unsigned long long *__restrict__ top, uint32_t K, unsigned long long *__restrict__ cand,
+                                uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n,
+                                const Rerank &rr, unsigned long long *sk) {
+    const CandList cl(cand_cnt, q, cap);
+    const uint32_t n = cl.size();
+    if (n == 0) return;
+    unsigned long long *cq = cand + q * cap;
+    if (rr.base) {
+        float *sq = reinterpret_cast<float *>(sk + sort_n);  // dim floats after the sort buffer
+        for (uint32_t j = threadIdx.x; j < rr.dim; j += blockDim.x) sq[j] = rr.queries[q * rr.dim + j];
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const float qq = rr.metric_l2 ? rr.qn[q] : 0.f;
+        // four candidates per warp pass: their row loads are independent, so the DRAM latencies overlap
+        for (uint32_t i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
+            uint32_t b[4];
+            const float *br[4];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                b[t] = (uint32_t)cq[cl.slot(min(i0 + t, n - 1))];
+                br[t] = rr.base + (uint64_t)b[t] * rr.dim;
+            }
+            for (uint32_t j = lane; j < rr.dim; j += 32) {
+                const float qv = sq[j];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] = fmaf(qv, __ldg(br[t] + j), acc[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+            __syncwarp();
+            if (lane < 4 && i0 + lane < n) {
+                const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+                const uint32_t bb = lane == 0 ? b[0] : lane == 1 ? b[1] : lane == 2 ? b[2] : b[3];
+                const float d = rr.metric_l2 ? (-2.0f * a + rr.bn[bb]) + qq : -a;
+                cq[cl.slot(i0 + lane)] = ((unsigned long long)f2ord(d) << 32) | bb;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    // smallest power of two holding n + K
+    uint32_t m = 1;
+    while (m < n + K) m <<= 1;
+    if (m > sort_n) m = sort_n;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        unsigned long long v = ~0ull;
+        if (i < n) v = cq[cl.slot(i)];
+        else if (i < n + K) v = top[q * K + (i - n)];
+        sk[i] = v;
+    }
+    __syncthreads();
+    bitonic_sort_smem(sk, m);
     for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) top[q * K + i] = sk[i];
     if (threadIdx.x == 0) {
         const unsigned long long kth = sk[K - 1];
         tau[q] = (kth == ~0ull) ? INFINITY : ord2f((uint32_t)(kth >> 32));
-        cand_cnt[q] = 0;
+        cand_cnt[2 * q] = 0;
+        cand_cnt[2 * q + 1] = 0;
+    }
+    __syncthreads();
+}
+
+// work_cnt == nullptr: one CTA per query (blockIdx.x); otherwise the CTAs walk the work list left by the fast kernel
+__global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t K, unsigned long long *__restrict__ cand,
+                                 uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n,
+                                 const Rerank rr, const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ work_cnt) {
+    extern __shared__ unsigned long long sk[];
+    if (!work_cnt) {
+        merge_query_big(blockIdx.x, top, K, cand, cand_cnt, cap, tau, sort_n, rr, sk);
+        return;
+    }
+    const uint32_t nw = *work_cnt;
+    for (uint32_t w = blockIdx.x; w < nw; w += gridDim.x) merge_query_big(worklist[w], top, K, cand, cand_cnt, cap, tau, sort_n, rr, sk);
+}
+
+// Fast path of the tensor-core pipeline (candidates carry ids only): one CTA of 128 threads per query, at most `sn` - K
+// candidates (more: the query goes to the work list of the general kernel).  Exact fp32 distances of eight candidates per
+// warp pass (128-bit row loads when VEC), candidates that do not beat the current K-th best are dropped before the sort,
+// and the sort buffer holds only `sn` words, so sixteen queries are resident per SM and the gather latencies overlap.
+template <bool VEC>
+__global__ void __launch_bounds__(128) knn_merge_fast_kernel(unsigned long long *__restrict__ top, uint32_t K,
+                                                             const unsigned long long *__restrict__ cand,
+                                                             uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau,
+                                                             uint32_t sn, const Rerank rr, uint32_t *__restrict__ worklist,
+                                                             uint32_t *__restrict__ work_cnt) {
+    extern __shared__ unsigned long long sk[];
+    __shared__ uint32_t s_kept;
+    const uint64_t q = blockIdx.x;
+    const CandList cl(cand_cnt, q, cap);
+    const uint32_t n = cl.size();
+    if (n == 0) return;
+    if (n + K > sn) {
+        if (threadIdx.x == 0) worklist[atomicAdd(work_cnt, 1u)] = (uint32_t)q;
+        return;
+    }
+    float *sq = reinterpret_cast<float *>(sk + sn);
+    if (VEC) {
+        const float4 *q4 = reinterpret_cast<const float4 *>(rr.queries + q * rr.dim);
+        for (uint32_t j = threadIdx.x; j < rr.dim / 4; j += blockDim.x) reinterpret_cast<float4 *>(sq)[j] = q4[j];
+    } else {
+        for (uint32_t j = threadIdx.x; j < rr.dim; j += blockDim.x) sq[j] = rr.queries[q * rr.dim + j];
+    }
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    const unsigned long long kth = top[q * K + K - 1];  // (distance, id) of the current K-th best, ~0 while the list is short
+    const unsigned long long *cq = cand + q * cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float qq = rr.metric_l2 ? rr.qn[q] : 0.f;
+    for (uint32_t i0 = warp * 8; i0 < n; i0 += 32) {
+        uint32_t myb = 0;
+        if (lane < 8 && i0 + lane < n) myb = (uint32_t)cq[cl.slot(i0 + lane)];
+        float acc[8];
+        uint32_t b[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            b[t] = __shfl_sync(0xffffffffu, myb, t);  // tail slots repeat row 0 of the base: harmless, dropped below
+            acc[t] = 0.f;
+        }
+        if (VEC) {
+            for (uint32_t j = lane; j < rr.dim / 4; j += 32) {
+                const float4 qv = reinterpret_cast<const float4 *>(sq)[j];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float4 x = __ldg(reinterpret_cast<const float4 *>(rr.base + (uint64_t)b[t] * rr.dim) + j);
+                    acc[t] = fmaf(qv.x, x.x, acc[t]);
+                    acc[t] = fmaf(qv.y, x.y, acc[t]);
+                    acc[t] = fmaf(qv.z, x.z, acc[t]);
+                    acc[t] = fmaf(qv.w, x.w, acc[t]);
+                }
+            }
+        } else {
+            for (uint32_t j = lane; j < rr.dim; j += 32) {
+                const float qv = sq[j];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] = fmaf(qv, __ldg(rr.base + (uint64_t)b[t] * rr.dim + j), acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        float a = acc[0];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) a = lane == t ? acc[t] : a;
+        bool keep = false;
+        unsigned long long key = 0;
+        if (lane < 8 && i0 + lane < n) {
+            const float d = rr.metric_l2 ? (-2.0f * a + rr.bn[myb]) + qq : -a;
+            key = ((unsigned long long)f2ord(d) << 32) | myb;
+            keep = key < kth;
+        }
+        const uint32_t vote = __ballot_sync(0xffffffffu, keep);
+        uint32_t base_slot = 0;
+        if (lane == 0 && vote) base_slot = atomicAdd(&s_kept, (uint32_t)__popc(vote));
+        base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+        if (keep) sk[base_slot + __popc(vote & ((1u << lane) - 1u))] = key;
+    }
+    __syncthreads();
+    const uint32_t kept = s_kept;
+    if (kept) {
+        uint32_t m = 1;
+        while (m < kept + K) m <<= 1;  // <= sn because kept <= n
+        for (uint32_t i = kept + threadIdx.x; i < m; i += blockDim.x) sk[i] = i < kept + K ? top[q * K + (i - kept)] : ~0ull;
+        __syncthreads();
+        bitonic_sort_smem(sk, m);
+        for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) top[q * K + i] = sk[i];
+    }
+    if (threadIdx.x == 0) {
+        if (kept) {
+            const unsigned long long nk = sk[K - 1];
+            tau[q] = (nk == ~0ull) ? INFINITY : ord2f((uint32_t)(nk >> 32));
+        }
+        cand_cnt[2 * q] = 0;
+        cand_cnt[2 * q + 1] = 0;
     }
 }
 
@@ -211,7 +351,8 @@ __global__ void knn_init_kernel(unsigned long long *top, uint64_t n_top, float *
     if (i < n_top) top[i] = ~0ull;
     if (i < nq) {
         tau[i] = INFINITY;
-        cnt[i] = 0;
+        cnt[2 * i] = 0;
+        cnt[2 * i + 1] = 0;
     }
 }
 
@@ -294,7 +435,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
         if (fit) qb_max = fit;
     }
 
-    Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf, s_b16, s_q16, s_max;
+    Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf, s_b16, s_q16, s_max, s_work;
     float *bn = nullptr, *qn = nullptr;
     const float *B = d_base, *Q = d_queries;
     if (metric_l2 || tc) {  // the tensor-core filter needs the norms for its error bound even for inner product
@@ -341,13 +482,22 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     const size_t merge_smem = (size_t)sort_n * 8 + (tc ? (size_t)dim * 4 : 0);
     RG_CUDA(cudaMalloc(&s_top.p, qb_alloc * K * sizeof(unsigned long long)));
     RG_CUDA(cudaMalloc(&s_cand.p, qb_alloc * cap * sizeof(unsigned long long)));
-    RG_CUDA(cudaMalloc(&s_cnt.p, qb_alloc * sizeof(uint32_t)));
+    RG_CUDA(cudaMalloc(&s_cnt.p, 2 * qb_alloc * sizeof(uint32_t)));
+    RG_CUDA(cudaMalloc(&s_work.p, (qb_alloc + 1) * sizeof(uint32_t)));
     RG_CUDA(cudaMalloc(&s_tau.p, qb_alloc * sizeof(float)));
     RG_CUDA(cudaMalloc(&s_ovf.p, sizeof(uint32_t)));
     unsigned long long *top = (unsigned long long *)s_top.p, *cand = (unsigned long long *)s_cand.p;
     uint32_t *cnt = (uint32_t *)s_cnt.p, *ovf = (uint32_t *)s_ovf.p;
     float *tau = (float *)s_tau.p;
     RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
+    uint32_t fast_sn = 512;
+    while (fast_sn < 4u * K) fast_sn <<= 1;
+    if (fast_sn > sort_n) fast_sn = sort_n;
+    const size_t fast_smem = (size_t)fast_sn * 8 + (size_t)dim * 4;
+    const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
+    RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    uint32_t *worklist = (uint32_t *)s_work.p, *work_cnt = worklist + qb_alloc;
 
     for (uint64_t qs = 0; qs < nq; qs += qb_max) {
         const uint64_t nqb = std::min<uint64_t>(qb_max, nq - qs);
@@ -375,7 +525,16 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
                     knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
                                                                         bn, metric_l2, tau, cand, cnt, cap, ovf);
                 }
-                knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr);
+                if (tc) {
+                    // fast path per query, then the general kernel over the (normally empty) work list of long lists
+                    RG_CUDA(cudaMemsetAsync(work_cnt, 0, sizeof(uint32_t), s));
+                    if (vec) knn_merge_fast_kernel<true><<<(unsigned)nqb, 128, fast_smem, s>>>(top, K, cand, cnt, cap, tau, fast_sn, rr, worklist, work_cnt);
+                    else knn_merge_fast_kernel<false><<<(unsigned)nqb, 128, fast_smem, s>>>(top, K, cand, cnt, cap, tau, fast_sn, rr, worklist, work_cnt);
+                    knn_merge_kernel<<<(unsigned)std::min<uint64_t>(nqb, 2ull * sm_count()), 256, merge_smem, s>>>(
+                        top, K, cand, cnt, cap, tau, sort_n, rr, worklist, work_cnt);
+                } else {
+                    knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr, nullptr, nullptr);
+                }
                 if (attempt == 0 && lo > 0) csize = std::min<uint64_t>(csize * 2, 1ull << 22);
                 lo = hi;
             }

@@ -118,6 +118,73 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---- cluster / 2-CTA (cta_group::2) primitives -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 rem;\n"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n"
+        "}\n" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to the barrier of the pair's leader (even
+// rank): bit 24 of a shared::cluster address is the CTA's rank inside the pair.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y)
+        : "memory");
+}
+// tcgen05.commit of a 2-CTA MMA group: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// three-input maximum (FMNMX3 on sm_100): a 32-value maximum is 16 instructions in a depth-4 tree
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+    float a[12];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    a[10] = v[30];
+    a[11] = v[31];
+    const float b0 = fmax3(a[0], a[1], a[2]), b1 = fmax3(a[3], a[4], a[5]), b2 = fmax3(a[6], a[7], a[8]),
+                b3 = fmax3(a[9], a[10], a[11]);
+    return fmaxf(fmax3(b0, b1, b2), b3);
+}
+
 // K-major, 128-byte swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); version 1 (sm_100);
 // layout type 2 = SWIZZLE_128B.  The tile base must be 1024-byte aligned; a k-step of 16 bf16 advances the start by 32 B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -130,8 +197,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n, uint32_t m = kBlockM) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 struct TcParams {
@@ -148,6 +215,7 @@ struct TcParams {
     const float *qn;        // ||q||^2 (exact fp32)
     const float *bn;        // ||b||^2
     float bmax;             // max_b ||b||
+    float err_rel;          // |dot_bf16 - dot| <= err_rel * ||q|| * ||b||
     unsigned long long *cand;
     uint32_t *cand_cnt;
     uint32_t cap;
@@ -297,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
         if (qrow < p.nq) {
             const float t = p.tau[qrow];
             const float qq = p.qn[qrow];
-            const float E = 1.01f * 0.0078125f * sqrtf(qq) * p.bmax;  // (2u + u^2) ||q|| ||b||, u = 2^-8, with slack
+            const float E = p.err_rel * sqrtf(qq) * p.bmax;
             if (p.metric_l2) theta = (qq - t) - 2.f * E;               // keep iff 2 dot - ||b||^2 > theta
             else theta = (-t) - E;                                    // keep iff dot > theta
             if (t == INFINITY) theta = -INFINITY;
@@ -335,9 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rr[e]);
                 }
-                float m = v[0];
-#pragma unroll
-                for (int e = 1; e < 32; ++e) m = fmaxf(m, v[e]);
+                const float m = max32(v);
                 if (m > theta) {  // rare once tau has tightened
                     uint32_t mask = 0;
 #pragma unroll
@@ -347,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
                         mask &= mask - 1;
                         const uint64_t b = col0 + cc * 32 + e;
                         if (b < p.nb) {
-                            const uint32_t slot = atomic_append ? atomicAdd(p.cand_cnt + qrow, 1u) : cnt++;
+                            const uint32_t slot = atomic_append ? atomicAdd(p.cand_cnt + 2 * qrow, 1u) : cnt++;
                             if (slot < p.cap) p.cand[qrow * p.cap + slot] = (unsigned long long)(uint32_t)b;
                             else *p.overflow = 1u;
                         }
@@ -359,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        if (!atomic_append && qrow < p.nq && cnt) p.cand_cnt[qrow] = cnt;
+        if (!atomic_append && qrow < p.nq && cnt) p.cand_cnt[2 * qrow] = cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -367,6 +433,234 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ---- 2-CTA variant (the default) -----------------------------------------------------------------------------------------
+// A cluster of two CTAs on an SM pair runs ONE tcgen05.mma.cta_group::2 of shape M = 256 (128 queries per CTA) x N = 256
+// (base rows, 128 staged by each CTA) per k-step.  Per CTA and k-step the tensor core reads 4 KB of A and 4 KB of B from
+// shared memory in 128 cycles — half the shared-memory bandwidth of the 1-CTA 128 x 128 shape, which was the limiter of
+// the single-CTA kernel (tensor pipe 64 % with the MMA warp never waiting, profiles/r1_knn_tc_10M_ncu_full.txt) — while
+// the L2 -> SM operand traffic stays at 128 base rows per CTA and tile.  Each CTA keeps the accumulator rows of its own
+// 128 queries: 2 x 256 TMEM columns, double-buffered against the epilogue exactly as above.
+//   barriers:  full[s]   leader only, 2 arrivals (the leader's expect_tx + the peer's remote arrive) + both CTAs' TMA bytes
+//              empty[s]  both CTAs, arrived by the multicast tcgen05.commit of the MMAs that read the stage
+//              tfull[b]  both CTAs, multicast commit after a tile's last MMA
+//              tempty[b] leader only, 16 arrivals (8 epilogue warps x 2 CTAs)
+constexpr int kPairN = 256;                                    // UMMA N of the pair = base rows per tile
+constexpr uint32_t kPairBBytesPerKb = (kPairN / 2) * kBlockK * 2;  // each CTA stages half of the tile's rows: 16 KB
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    constexpr uint32_t kIdesc = make_idesc(kPairN, 2 * kBlockM);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (identical offsets in both CTAs): [A: num_kb x 16 KB][B ring: stages x 16 KB][bn: 2 x 256 floats][barriers][tmem ptr]
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + (size_t)p.num_kb * kABytesPerKb;
+    float *s_bn = reinterpret_cast<float *>(sB + (size_t)p.stages * kPairBBytesPerKb);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_bn + 2 * kPairN);
+    const uint32_t S = p.stages;
+    const uint32_t bar_a = smem_u32(bars);
+    const uint32_t bar_full = bar_a + 8;
+    const uint32_t bar_empty = bar_full + 8 * S;
+    const uint32_t bar_tfull = bar_empty + 8 * S;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 1 + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint64_t q0 = (uint64_t)blockIdx.x * kBlockM;  // blockIdx.x = 2 * pair + rank
+    const uint32_t t_begin = p.tile_lo + blockIdx.y * p.tiles_per_cta;
+    const uint32_t t_end = min(p.tile_hi, t_begin + p.tiles_per_cta);
+    const uint32_t n_tiles = t_end > t_begin ? t_end - t_begin : 0;
+
+    cluster_sync_all();  // both CTAs are resident before the pair-wide TMEM allocation
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 2);
+        for (uint32_t s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 2);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 16);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs performs the pair-wide allocation of all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // TMA producer of this CTA: its 128 query rows once, then its 128-row half of every base tile
+        if (n_tiles) {
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(bar_a, 2 * p.num_kb * kABytesPerKb);
+                else mbar_arrive_remote(bar_a, 0);
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb)
+                    tma_load_2d_pair(smem_u32(sA + (size_t)kb * kABytesPerKb), &map_q, bar_a, (int)(kb * kBlockK), (int)q0);
+            }
+            __syncwarp();
+            uint32_t stage = 0, phase = 0;
+            const uint32_t sB_u32 = smem_u32(sB);
+            for (uint32_t t = t_begin; t < t_end; ++t) {
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * kPairBBytesPerKb);
+                        else mbar_arrive_remote(bar_full + 8 * stage, 0);
+                        tma_load_2d_pair(sB_u32 + stage * kPairBBytesPerKb, &map_b, bar_full + 8 * stage, (int)(kb * kBlockK),
+                                         (int)(t * kPairN + rank * (kPairN / 2)));
+                    }
+                    __syncwarp();
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // MMA issuer: only the leader CTA issues; the instruction reads both CTAs' shared memory at the same offsets and
+        // writes both CTAs' TMEM
+        if (n_tiles && leader) {
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            const uint64_t d0 = umma_desc_sw128(0);
+            const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)d0 | ((smem_u32(sA) & 0x3ffffu) >> 4);
+            const uint32_t b_lo0 = (uint32_t)d0 | ((smem_u32(sB) & 0x3ffffu) >> 4);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t i = 0; i < n_tiles; ++i) {
+                const uint32_t buf = i & 1;
+                mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * kAccCols;
+                for (uint32_t kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + kb * (kABytesPerKb >> 4);
+                    const uint32_t b_lo = b_lo0 + stage * (kPairBBytesPerKb >> 4);
+                    const uint32_t nk = (kb == p.num_kb - 1) ? p.ksteps_last : (uint32_t)(kBlockK / kUmmaK);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                            if ((uint32_t)k < nk)
+                                tc_mma_bf16_pair(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, kIdesc, k == 0 ? (kb != 0 ? 1u : 0u) : 1u);
+                        tc_commit_pair(bar_empty + 8 * stage);  // frees the stage in both CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (elect_one()) tc_commit_pair(bar_tfull + 8 * buf);  // accumulator complete in both CTAs
+                __syncwarp();
+            }
+            // the peer's last remote arrivals must have landed before this CTA's barriers go away
+            for (uint32_t i = n_tiles > 2 ? n_tiles - 2 : 0; i < n_tiles; ++i) mbar_wait(bar_tempty + 8 * (i & 1), (i >> 1) & 1);
+        }
+    } else {
+        // epilogue, 8 warps per CTA: TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4.  A thread owns one
+        // query row and 128 of the tile's 256 columns; the two halves of a row append through the global counter.
+        const uint32_t quad = (uint32_t)warp & 3u;
+        const uint32_t half = (uint32_t)(warp - 2) >> 2;
+        const uint32_t row = quad * 32 + lane;
+        const int epi_tid = threadIdx.x - 64;  // 0..255
+        const uint64_t qrow = q0 + row;
+        const uint32_t sub_cap = p.cap >> 1;
+        unsigned long long *my_cand = p.cand + qrow * p.cap + half * sub_cap;
+        uint32_t cnt = 0;
+        float theta = INFINITY;  // rows past the batch never pass
+        if (qrow < p.nq) {
+            const float t = p.tau[qrow];
+            const float qq = p.qn[qrow];
+            const float E = p.err_rel * sqrtf(qq) * p.bmax;
+            if (p.metric_l2) theta = (qq - t) - 2.f * E;  // keep iff 2 dot - ||b||^2 > theta
+            else theta = (-t) - E;                        // keep iff dot > theta
+            if (t == INFINITY) theta = -INFINITY;
+        }
+        for (uint32_t i = 0; i < n_tiles; ++i) {
+            const uint32_t buf = i & 1;
+            const uint32_t tile = t_begin + i;
+            const uint64_t col0 = (uint64_t)tile * kPairN + half * 128u;
+            if (p.metric_l2) {
+                for (int j = epi_tid; j < kPairN; j += 256) {
+                    const uint64_t b = (uint64_t)tile * kPairN + j;
+                    s_bn[buf * kPairN + j] = b < p.nb ? __ldg(p.bn + b) : 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kAccCols + half * 128u;
+            uint32_t r[2][32];
+            __syncwarp();
+            tc_ld32(taddr, r[0]);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                tc_ld_wait();
+                if (cc + 1 < 4) tc_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // overlaps the scan below
+                const uint32_t(&rr)[32] = r[cc & 1];
+                float v[32];
+                if (p.metric_l2) {
+                    const float4 *bn4 = reinterpret_cast<const float4 *>(s_bn + buf * kPairN + half * 128u + cc * 32);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 b4 = bn4[e];
+                        v[4 * e + 0] = fmaf(2.f, __uint_as_float(rr[4 * e + 0]), -b4.x);
+                        v[4 * e + 1] = fmaf(2.f, __uint_as_float(rr[4 * e + 1]), -b4.y);
+                        v[4 * e + 2] = fmaf(2.f, __uint_as_float(rr[4 * e + 2]), -b4.z);
+                        v[4 * e + 3] = fmaf(2.f, __uint_as_float(rr[4 * e + 3]), -b4.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rr[e]);
+                }
+                if (max32(v) > theta) {  // rare once tau has tightened
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mask |= (v[e] > theta ? 1u : 0u) << e;
+                    while (mask) {
+                        const int e = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint64_t b = col0 + cc * 32 + e;
+                        if (b < p.nb) {
+                            if (p.atomic_append) {  // few queries: the base range is split over blockIdx.y, lists are shared
+                                const uint32_t slot = atomicAdd(p.cand_cnt + 2 * qrow, 1u);
+                                if (slot < p.cap) p.cand[qrow * p.cap + slot] = (unsigned long long)(uint32_t)b;
+                                else *p.overflow = 1u;
+                            } else {  // private sub-list of this (query, column half): no atomic, no round trip
+                                if (cnt < sub_cap) my_cand[cnt] = (unsigned long long)(uint32_t)b;
+                                else *p.overflow = 1u;
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();  // tcgen05.ld / wait are .sync.aligned: reconverge after a divergent survivor scan
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+        }
+        if (!p.atomic_append && qrow < p.nq && cnt) p.cand_cnt[2 * qrow + half] = cnt;
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -482,6 +776,37 @@ static int launch_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, ui
     return RG_OK;
 }
 
+
+// 2-CTA launch: grid.x = 2 CTAs per 256 queries (one cluster), grid.y = base-range splits when there are few queries.
+static int launch_filter_pair(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t kp, uint64_t row_lo,
+                              uint64_t row_hi, TcParams p, int sm_count, cudaStream_t s) {
+    CUtensorMap map_q, map_b;
+    int rc = make_map(&map_q, q_bf16, nq, kp, kBlockM);
+    if (rc != RG_OK) return rc;
+    rc = make_map(&map_b, b_bf16, nb, kp, kPairN / 2);
+    if (rc != RG_OK) return rc;
+    const size_t fixed = (size_t)p.num_kb * kABytesPerKb + 2 * kPairN * 4 + 512 + 1024;
+    const size_t budget = 227 * 1024;
+    uint32_t stages = (uint32_t)((budget - fixed) / kPairBBytesPerKb);
+    if (stages > 12) stages = 12;
+    p.stages = stages;
+    p.tile_lo = (uint32_t)(row_lo / kPairN);
+    p.tile_hi = (uint32_t)((row_hi + kPairN - 1) / kPairN);
+    const uint32_t tiles = p.tile_hi - p.tile_lo;
+    const uint32_t q_ctas = 2u * (uint32_t)((nq + 2 * kBlockM - 1) / (2 * kBlockM));
+    uint32_t splits = 1;
+    if (q_ctas < 2u * (uint32_t)sm_count) splits = std::min<uint32_t>(tiles, (2u * (uint32_t)sm_count + q_ctas - 1) / q_ctas);
+    p.tiles_per_cta = (tiles + splits - 1) / splits;
+    splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    p.atomic_append = splits > 1 ? 1 : 0;
+    const size_t smem = fixed + (size_t)stages * kPairBBytesPerKb;
+    RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(q_ctas, splits);
+    knn_tc_filter_pair_kernel<<<grid, kThreads, smem, s>>>(map_q, map_b, p);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
 int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
                   int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
                   uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s) {
@@ -500,8 +825,12 @@ int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t 
     p.cand_cnt = cand_cnt;
     p.cap = cap;
     p.overflow = overflow;
+    p.err_rel = 1.01f * 0.0078125f;  // (2u + u^2) with u = 2^-8 (bf16 round-to-nearest), plus slack for the fp32 accumulation
+    // RG_KNN_QTILES=1|2 selects the single-CTA kernels (one or two resident query tiles); default: the 2-CTA kernel
     const char *force = getenv("RG_KNN_QTILES");
-    const bool two = force ? force[0] == '2' : (p.num_kb <= 4 && nq > (uint64_t)kBlockM);
+    if (!force || (force[0] != '1' && force[0] != '2'))
+        return launch_filter_pair(q_bf16, nq, b_bf16, nb, kp, row_lo, row_hi, p, sm_count, s);
+    const bool two = force[0] == '2';
     if (two && p.num_kb <= 4) return launch_filter<2>(q_bf16, nq, b_bf16, nb, kp, row_lo, row_hi, p, sm_count, s);
     return launch_filter<1>(q_bf16, nq, b_bf16, nb, kp, row_lo, row_hi, p, sm_count, s);
 }

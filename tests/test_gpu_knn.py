@@ -9,10 +9,15 @@ from test_oracle_golden import check_knn
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc", "simt"], autouse=True)
+@pytest.fixture(params=["tc", "tc1", "tc2", "simt"], autouse=True)
 def knn_mode(request, monkeypatch):
-    """Every test runs through both candidate filters: the tcgen05 bf16 tile (default) and the fp32 SIMT tile."""
-    monkeypatch.setenv("RG_KNN_MODE", request.param)
+    """Every test runs through every candidate filter: the 2-CTA tcgen05 bf16 kernel (default), the single-CTA tcgen05
+    kernels with one / two resident query tiles, and the fp32 SIMT tile."""
+    monkeypatch.setenv("RG_KNN_MODE", "simt" if request.param == "simt" else "tc")
+    if request.param in ("tc1", "tc2"):
+        monkeypatch.setenv("RG_KNN_QTILES", request.param[2])
+    else:
+        monkeypatch.delenv("RG_KNN_QTILES", raising=False)
     return request.param
 
 
