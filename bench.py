@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--cache_dir", default=os.environ.get("RG_BENCH_CACHE", "/tmp/rg_bench_cache"))
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_knn", action="store_true", help="skip the brute-force kNN leg")
     ap.add_argument("--sweep", default="", help="also write the full L_pq sweep table (CSV) to this path")
     return ap.parse_args()
 
@@ -130,6 +131,51 @@ def workload_name(a):
     label = "t2i" if (a.dim == 200 and a.dist == "ip") else ("laion" if a.dim == 512 else "synthetic")
     return (f"{label}-like synthetic {a.nb}x{a.dim} {a.dist}, {a.nq} queries top-{a.k}, RoarGraph M_sq={a.M_sq} "
             f"M_pjbp={a.M_pjbp} L_pjpq={a.L_pjpq} from {a.ntrain} training queries")
+
+
+def load_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md, sustained)"
+
+
+def time_knn(a, w, dev, world, K=100, reps=2):
+    """BASELINE.json's second metric: brute-force training-query x base kNN pairs/s (compute_groundtruth's exact_knn),
+    base sharded over the ranks like the search (configs[3]): local tcgen05 filter + exact re-rank, all-gather, merge."""
+    import torch
+    import torch.distributed as dist
+
+    from roargraph_b200.sharded import sharded_knn_dev
+
+    q = w.d_train_sample
+    metric = "l2" if a.dist == "l2" else "ip"
+    best = None
+    for _ in range(reps + 1):  # first pass = warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ids, dists = sharded_knn_dev(w.d_base, q, K, metric, w.row_lo)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        best = dt if best is None else min(best, dt)
+        del ids, dists
+    pairs = float(q.shape[0]) * float(w.nd_total)
+    peak, src = load_tensor_peak()
+    tf = 2.0 * pairs * a.dim / best / 1e12
+    return {"metric": "brute-force kNN pairs/s", "value": pairs / best, "unit": "pairs/s", "nq": int(q.shape[0]),
+            "nb": int(w.nd_total), "dim": a.dim, "K": K, "dist": metric, "seconds": best, "tflops": tf,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak * world, "unit": "TFLOP/s",
+                         "frac": tf / (peak * world), "peak_source": src,
+                         "kernel": "knn_tc_filter_pair_kernel (tcgen05 bf16 filter) + knn_merge_fast_kernel (fp32 re-rank)"},
+            "note": "wall clock of the whole call: fp32->bf16 conversion, norms, every filter and merge launch"
+                    + (", all-gather + k-way merge over the shards" if world > 1 else "")}
 
 
 def time_reference_cpu(a, w, L, want_sample_s=15.0):
@@ -307,6 +353,13 @@ def main():
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (kern_avg_ms / 1e3) / 1e9
 
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this very workload, if there is one
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{a.nb}x{a.dim}:{a.dist}:L{L}", {}).get("traffic_bytes") if world == 1 else None
+    except OSError:
+        pass
+
     # ---- end to end through the C-ABI host-buffer call ---------------------------------------------------------------
     hq = torch.from_numpy(w.queries_host).pin_memory()
     h_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
@@ -371,6 +424,13 @@ def main():
                 f.write(",".join(f"{x:.6g}" for x in r) + "\n")
         sweep_table = a.sweep
 
+    knn_out = None
+    if not a.no_knn:
+        try:
+            knn_out = time_knn(a, w, dev, world)
+        except Exception as e:  # noqa: BLE001
+            knn_out = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
@@ -398,9 +458,10 @@ def main():
                     "ms_per_step": float(np.mean(e2e_ms))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "beam_search_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "beam_search_kernel",
                          "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": int(alg_bytes)},
             "cpu_baseline": cpu_out,
+            "knn": knn_out,
         }
         if sweep_table:
             line["config"]["sweep_csv"] = sweep_table

@@ -490,7 +490,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     uint32_t *cnt = (uint32_t *)s_cnt.p, *ovf = (uint32_t *)s_ovf.p;
     float *tau = (float *)s_tau.p;
     RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
-    uint32_t fast_sn = 512;
+    uint32_t fast_sn = 1024;
     while (fast_sn < 4u * K) fast_sn <<= 1;
     if (fast_sn > sort_n) fast_sn = sort_n;
     const size_t fast_smem = (size_t)fast_sn * 8 + (size_t)dim * 4;
@@ -535,8 +535,11 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
                 } else {
                     knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr, nullptr, nullptr);
                 }
-                if (attempt == 0 && lo > 0) csize = std::min<uint64_t>(csize * 2, 1ull << 22);
                 lo = hi;
+                // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
+                // still fit in L2 (tensor-core path: the re-rank gather of those ~3K survivors never reaches DRAM, and
+                // the fixed per-launch cost of filter + merge dominates there)
+                if (attempt == 0) csize = std::min<uint64_t>((tc && lo < 65536) ? 3 * lo : lo, 1ull << 22);
             }
             RG_CUDA(cudaGetLastError());
             uint32_t h_ovf = 0;

@@ -174,15 +174,33 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
-__device__ __forceinline__ float max32(const float (&v)[32]) {
-    float a[12];
+// maximum of 32 values; g[0..3] = maxima of v[0..8], v[9..17], v[18..26], v[27..31] (the survivor scan descends only into
+// groups that hold a survivor)
+__device__ __forceinline__ float max32(const float (&v)[32], float (&g)[4]) {
+    float a[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-    a[10] = v[30];
-    a[11] = v[31];
-    const float b0 = fmax3(a[0], a[1], a[2]), b1 = fmax3(a[3], a[4], a[5]), b2 = fmax3(a[6], a[7], a[8]),
-                b3 = fmax3(a[9], a[10], a[11]);
-    return fmaxf(fmax3(b0, b1, b2), b3);
+    g[0] = fmax3(a[0], a[1], a[2]);
+    g[1] = fmax3(a[3], a[4], a[5]);
+    g[2] = fmax3(a[6], a[7], a[8]);
+    g[3] = fmax3(a[9], v[30], v[31]);
+    return fmaxf(fmax3(g[0], g[1], g[2]), g[3]);
+}
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+    float g[4];
+    return max32(v, g);
+}
+// bit e set iff v[e] > theta, looking only inside the groups whose maximum passes
+__device__ __forceinline__ uint32_t survivor_mask(const float (&v)[32], const float (&g)[4], float theta) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (g[k] > theta) {
+#pragma unroll
+            for (int e = 9 * k; e < (k == 3 ? 32 : 9 * k + 9); ++e) mask |= (v[e] > theta ? 1u : 0u) << e;
+        }
+    }
+    return mask;
 }
 
 // K-major, 128-byte swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); version 1 (sm_100);
@@ -627,10 +645,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rr[e]);
                 }
-                if (max32(v) > theta) {  // rare once tau has tightened
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) mask |= (v[e] > theta ? 1u : 0u) << e;
+                float gmax[4];
+                if (max32(v, gmax) > theta) {  // rare once tau has tightened
+                    uint32_t mask = survivor_mask(v, gmax, theta);
                     while (mask) {
                         const int e = __ffs(mask) - 1;
                         mask &= mask - 1;

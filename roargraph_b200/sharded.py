@@ -89,3 +89,40 @@ class ShardedRoarIndex:
         dists = out_d.cpu().numpy()
         self.index.check(torch.cuda.current_stream())
         return ids, dists
+
+
+def sharded_knn_dev(d_base_shard, d_queries, K: int, metric, row_lo: int, group=None, batch: int = 1 << 20,
+                    local_knn=None, merge=None):
+    """Brute-force kNN with the BASE sharded over the ranks of `group` (BASELINE.json configs[3]): every rank scores all
+    queries against its base rows [row_lo, row_lo + nb_local) — the parts of compute_groundtruth.cpp:396-416, ids offset
+    by the part's start (:413) — then, per query batch, ONE all-gather of the per-shard (distance, id)[batch][K] lists
+    and the k-way merge kernel (the std::sort merge of :424-444) give the global top-K on every rank.
+
+    d_base_shard / d_queries: device tensors (fp32, row-major).  Returns (ids int32 [nq, K], dists fp32 [nq, K]) on the
+    device: internal distances ascending (-IP for "ip", squared L2 for "l2"/"cosine"), global ids.
+    `local_knn` / `merge` default to the CUDA entry points (rg.knn_dev, rg.topk_merge_dev); the CPU tests inject
+    checkers there to exercise the batching, offsets and collective layout over gloo."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    nq = d_queries.shape[0]
+    dev = d_queries.device
+    if local_knn is None:
+        def local_knn(b, q, k, m, ids, dists, id_offset):
+            rg.knn_dev(b, q, k, m, ids, dists, id_offset=id_offset, stream=torch.cuda.current_stream())
+    if merge is None:
+        def merge(all_d, all_i, out_d, out_i):
+            rg.topk_merge_dev(all_d, all_i, out_d, out_i, stream=torch.cuda.current_stream())
+    loc_i = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    loc_d = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    local_knn(d_base_shard, d_queries, K, metric, loc_i, loc_d, int(row_lo))
+    if world == 1:
+        return loc_i, loc_d
+    out_i = torch.empty_like(loc_i)
+    out_d = torch.empty_like(loc_d)
+    for lo in range(0, nq, batch):
+        hi = min(nq, lo + batch)
+        all_d, all_i = gather_topk(loc_d[lo:hi], loc_i[lo:hi], group)
+        merge(all_d, all_i, out_d[lo:hi], out_i[lo:hi])
+    return out_i, out_d

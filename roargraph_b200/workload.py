@@ -68,6 +68,7 @@ class SearchWorkload:
         self.nd_total = 0
         self.metric = "ip"
         self.k = 10
+        self.d_train_sample = None # torch [<=151552, dim]: training queries kept for bench.py's brute-force kNN leg
         self.info = {}
 
 
@@ -155,6 +156,7 @@ def build_search_workload(nb: int, dim: int, metric: str, ntrain: int, nq: int, 
             tmp = cpath + f".tmp{os.getpid()}.npz"
             np.savez(tmp, ep=np.uint32(ep), row_off=row_off, nbrs=nbrs)
             os.replace(tmp, cpath)
+    w.d_train_sample = train[:min(ntrain, 151552)].clone()
     del train
     torch.cuda.empty_cache()
     g = w.index.graph_size()

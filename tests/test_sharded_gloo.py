@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import GoldenCase
-from roargraph_b200.sharded import gather_topk, shard_range
+from roargraph_b200.sharded import gather_topk, shard_range, sharded_knn_dev
 
 
 def _free_port():
@@ -67,3 +67,45 @@ def test_two_rank_gather_and_merge(tmp_path, oracle):
     full_i, full_d = oracle.exact_knn(g.base, g.queries, k, "ip")
     np.testing.assert_allclose(merged_d, full_d, rtol=1e-6, atol=1e-6)
     assert (merged_i == full_i).mean() > 0.999
+
+
+def _knn_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    O = Oracle()
+    g = GoldenCase("l2_d104")
+    nb = g.base_raw.shape[0]
+    lo, hi = shard_range(nb, rank, world)
+    K = 7
+
+    def local_knn(b, q, k, m, ids, dists, id_offset):  # checker standing in for rg.knn_dev on this rank's part
+        i, d = O.exact_knn(b.numpy(), q.numpy(), k, m)
+        ids.copy_(torch.from_numpy(i.astype(np.int32) + id_offset))
+        dists.copy_(torch.from_numpy(d))
+
+    def merge(all_d, all_i, out_d, out_i):  # (distance asc, id asc), as rg_topk_merge_dev
+        G, n, k = all_d.shape
+        d = all_d.numpy().transpose(1, 0, 2).reshape(n, G * k)
+        i = all_i.numpy().transpose(1, 0, 2).reshape(n, G * k)
+        order = np.lexsort((i, d), axis=1)[:, :k]
+        out_d.copy_(torch.from_numpy(np.take_along_axis(d, order, 1)))
+        out_i.copy_(torch.from_numpy(np.take_along_axis(i, order, 1)))
+
+    ids, dists = sharded_knn_dev(torch.from_numpy(g.base_raw[lo:hi]), torch.from_numpy(g.test_raw), K, "l2", lo, batch=17,
+                                 local_knn=local_knn, merge=merge)
+    if rank == 1:  # every rank holds the full answer
+        np.savez(out, d=dists.numpy(), i=ids.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_knn(tmp_path, oracle):
+    """Base parts on two ranks, ragged query batches (17 per all-gather): equals the single-part exact kNN."""
+    out = str(tmp_path / "knn.npz")
+    mp.spawn(_knn_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    z = np.load(out)
+    g = GoldenCase("l2_d104")
+    full_i, full_d = oracle.exact_knn(g.base_raw, g.test_raw, 7, "l2")
+    np.testing.assert_allclose(z["d"], full_d, rtol=1e-5, atol=1e-5)
+    assert (z["i"] == full_i).mean() > 0.999
