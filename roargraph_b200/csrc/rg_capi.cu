@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "rg_internal.h"
 
 namespace rg {
@@ -38,6 +40,13 @@ static int ensure_device() {
         return RG_ECUDA;
     }
     g_sm_count = prop.multiProcessorCount;
+    // The beam search gathers 800-byte / 2 KB rows at random: RG_L2_FETCH=32|64|128 sets the granularity at which L2
+    // fetches from HBM (a hint; the driver's default over-fetches around short rows)
+    if (const char *v = getenv("RG_L2_FETCH")) {
+        const size_t g = (size_t)strtoul(v, nullptr, 10);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+        cudaGetLastError();
+    }
     return RG_OK;
 }
 
@@ -380,7 +389,14 @@ static int search_host(rg_index *idx, bool bipartite, const float *q, uint32_t n
     if ((rc = idx->cmps.reserve(nq)) != RG_OK) return rc;
     if ((rc = idx->hops.reserve(nq)) != RG_OK) return rc;
     cudaStream_t s = idx->stream;
+    static const bool trace = getenv("RG_TRACE_E2E") != nullptr;  // per-phase device times of the host-buffer call, to stderr
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace) {
+        for (auto &e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], s);
+    }
     RG_CUDA(cudaMemcpyAsync(idx->q.p, q, (size_t)nq * idx->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (trace) cudaEventRecord(ev[1], s);
     const uint32_t *d_init = nullptr;
     if (bipartite && init_ids) {
         if ((rc = idx->init.reserve((size_t)nq * n_init)) != RG_OK) return rc;
@@ -390,11 +406,21 @@ static int search_host(rg_index *idx, bool bipartite, const float *q, uint32_t n
     rc = search_dev(idx, bipartite, idx->q.p, nq, k, L, d_init, n_init, seed, idx->ids.p, idx->dists.p, idx->cmps.p,
                     idx->hops.p, s);
     if (rc != RG_OK) return rc;
+    if (trace) cudaEventRecord(ev[2], s);
     RG_CUDA(cudaMemcpyAsync(ids, idx->ids.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     RG_CUDA(cudaMemcpyAsync(dists, idx->dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (cmps) RG_CUDA(cudaMemcpyAsync(cmps, idx->cmps.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     if (hops) RG_CUDA(cudaMemcpyAsync(hops, idx->hops.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (trace) cudaEventRecord(ev[3], s);
     RG_CUDA(cudaStreamSynchronize(s));
+    if (trace) {
+        float h2d = 0, kern = 0, d2h = 0;
+        cudaEventElapsedTime(&h2d, ev[0], ev[1]);
+        cudaEventElapsedTime(&kern, ev[1], ev[2]);
+        cudaEventElapsedTime(&d2h, ev[2], ev[3]);
+        fprintf(stderr, "[rg e2e] nq=%u h2d %.3f ms, search %.3f ms, d2h %.3f ms\n", nq, h2d, kern, d2h);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     return check_latched(idx);
 }
 
