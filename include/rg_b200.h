@@ -127,6 +127,10 @@ int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, ui
 int rg_knn_dev(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
                int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, void *stream);
 
+/* rg_knn / rg_knn_dev keep their device scratch (bf16 operand copies, candidate lists; a few GB at 10 M rows) in a
+ * grow-only per-process workspace so that repeated calls do not pay cudaMalloc/cudaFree; this gives it back. */
+int rg_knn_release_workspace(void);
+
 /* Merge G per-shard top-K lists per query (each ascending) into one ascending top-K:
  * the std::sort merge of compute_groundtruth.cpp:424-444 / the host merge of per-shard search results.
  * in_dists/in_ids: [G][nq][K] device arrays (e.g. an ncclAllGather result); out: [nq][K]. */

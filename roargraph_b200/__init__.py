@@ -263,6 +263,11 @@ def knn_dev(d_base, d_queries, K: int, metric: str | int, d_ids, d_dists, id_off
                             C.c_void_p(d_dists.data_ptr()), _stream_ptr(stream)))
 
 
+def knn_release_workspace() -> None:
+    """Free the device scratch rg_knn / rg_knn_dev keep between calls."""
+    _check(lib().rg_knn_release_workspace())
+
+
 def topk_merge_dev(d_in_dists, d_in_ids, d_out_dists, d_out_ids, stream=None) -> None:
     """[G, nq, K] per-shard lists -> [nq, K] merged (compute_groundtruth.cpp:424-444)."""
     G, nq, K = d_in_dists.shape

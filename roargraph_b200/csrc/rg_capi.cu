@@ -70,7 +70,14 @@ int rg::ensure_tags(rg_index *idx, uint32_t slots) {
     RG_CUDA(cudaMalloc(&idx->d_tags, bytes));
     RG_CUDA(cudaMalloc(&idx->d_slot_epoch, slots * sizeof(uint32_t)));
     RG_CUDA(cudaMemset(idx->d_tags, 0, bytes));
-    RG_CUDA(cudaMemset(idx->d_slot_epoch, 0, slots * sizeof(uint32_t)));
+    {
+        // Stagger the 8-bit epochs: a slot clears its whole tag array when the epoch wraps (VisitedList::reset), and
+        // slots that all started at 0 would all wrap inside the same launch (a 2-5x slower batch every ~90 batches of
+        // 10 000 queries); spread over the 255 phases the clears cost every launch the same ~1 %.
+        std::vector<uint32_t> e0(slots);
+        for (uint32_t i = 0; i < slots; ++i) e0[i] = (uint32_t)(((uint64_t)i * 97u) % 255u);
+        RG_CUDA(cudaMemcpy(idx->d_slot_epoch, e0.data(), slots * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     idx->n_slots = slots;
     return RG_OK;
 }
@@ -339,7 +346,7 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
         const char *pf = getenv("RG_PREFETCH_ADJ");
         // doubles as the adjacency-prefetch switch; off by default: at 24 resident warps per SM the extra L2 fills cost
         // more DRAM bandwidth than the shorter dependent read saves (profiles/r1_tune_10M.csv)
-        p.n_init = (pf && pf[0] == '1') ? 1u : 0u;
+        p.n_init = (pf && pf[0] == '1') ? 1u : (pf && pf[0] == '2') ? 2u : 0u;  // 1: on queue insertion, 2: the next-best node at hop start
     }
     p.queries = d_q;
     p.out_ids = d_ids;
@@ -489,6 +496,11 @@ int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, ui
     if (d_i) cudaFree(d_i);
     if (e != cudaSuccess) return cuda_fail(e, "rg_knn");
     return rc;
+}
+
+int rg_knn_release_workspace(void) {
+    knn_release_workspace();
+    return RG_OK;
 }
 
 int rg_topk_merge_dev(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,

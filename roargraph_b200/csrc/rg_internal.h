@@ -122,6 +122,7 @@ int ensure_tags(rg_index *idx, uint32_t slots);
 uint32_t affordable_slots(rg_index *idx);
 
 // tensor-core candidate filter of the kNN (rg_knn_tc.cu)
+void knn_release_workspace();
 bool knn_tc_supported(uint32_t dim);
 uint32_t knn_tc_pitch(uint32_t dim);
 int knn_tc_convert(const float *x, uint64_t n, uint32_t dim, void *out_bf16, float *sq, cudaStream_t s);

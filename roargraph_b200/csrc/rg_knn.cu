@@ -396,10 +396,50 @@ __global__ void topk_merge_kernel(const float *in_d, const uint32_t *in_i, uint3
     }
 }
 
-struct Scratch {
-    void *p = nullptr;
-    ~Scratch() { if (p) cudaFree(p); }
+// Scratch buffers of knn_device live in a grow-only per-process workspace: cudaMalloc / cudaFree of the multi-GB
+// candidate lists and the bf16 base copy cost ~10 % of a one-batch call, and a 10 M-query run re-enters with the same
+// sizes.  rg_knn_release_workspace() (knn_release_workspace) gives the memory back.
+struct Workspace {
+    static constexpr int kSlots = 16;
+    void *p[kSlots] = {};
+    size_t cap[kSlots] = {};
+    int device = -1;
+    void release() {
+        for (int i = 0; i < kSlots; ++i) {
+            if (p[i]) cudaFree(p[i]);
+            p[i] = nullptr;
+            cap[i] = 0;
+        }
+    }
+    int get(int slot, size_t bytes, void **out) {
+        int dev = 0;
+        RG_CUDA(cudaGetDevice(&dev));
+        if (dev != device) {
+            release();
+            device = dev;
+        }
+        if (cap[slot] < bytes) {
+            if (p[slot]) cudaFree(p[slot]);
+            p[slot] = nullptr;
+            cap[slot] = 0;
+            RG_CUDA(cudaMalloc(&p[slot], bytes));
+            cap[slot] = bytes;
+        }
+        *out = p[slot];
+        return RG_OK;
+    }
 };
+Workspace g_ws;
+enum { WS_BN, WS_QN, WS_BCOPY, WS_QCOPY, WS_TOP, WS_CAND, WS_CNT, WS_TAU, WS_OVF, WS_B16, WS_Q16, WS_MAX, WS_WORK };
+
+struct Scratch {  // a view of one workspace slot
+    void *p = nullptr;
+};
+#define RG_WS(scr, slot, bytes)                                        \
+    do {                                                               \
+        int rc_ws_ = g_ws.get(slot, (size_t)(bytes), &(scr).p);        \
+        if (rc_ws_ != RG_OK) return rc_ws_;                            \
+    } while (0)
 
 }  // namespace
 
@@ -439,15 +479,15 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     float *bn = nullptr, *qn = nullptr;
     const float *B = d_base, *Q = d_queries;
     if (metric_l2 || tc) {  // the tensor-core filter needs the norms for its error bound even for inner product
-        RG_CUDA(cudaMalloc(&s_bn.p, nb * sizeof(float)));
-        RG_CUDA(cudaMalloc(&s_qn.p, nq * sizeof(float)));
+        RG_WS(s_bn, WS_BN, nb * sizeof(float));
+        RG_WS(s_qn, WS_QN, nq * sizeof(float));
         bn = (float *)s_bn.p;
         qn = (float *)s_qn.p;
         row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(d_base, nb, dim, bn);
         row_sqnorm_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(d_queries, nq, dim, qn);
         if (cosine) {
-            RG_CUDA(cudaMalloc(&s_bcopy.p, nb * dim * sizeof(float)));
-            RG_CUDA(cudaMalloc(&s_qcopy.p, nq * dim * sizeof(float)));
+            RG_WS(s_bcopy, WS_BCOPY, nb * dim * sizeof(float));
+            RG_WS(s_qcopy, WS_QCOPY, nq * dim * sizeof(float));
             row_normalize_kernel<<<(unsigned)((nb * dim + 255) / 256), 256, 0, s>>>(d_base, nb, dim, bn, (float *)s_bcopy.p);
             row_normalize_kernel<<<(unsigned)((nq * dim + 255) / 256), 256, 0, s>>>(d_queries, nq, dim, qn, (float *)s_qcopy.p);
             B = (const float *)s_bcopy.p;
@@ -460,9 +500,9 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     float bmax = 0.f;
     if (tc) {
         const uint32_t kp = knn_tc_pitch(dim);
-        RG_CUDA(cudaMalloc(&s_b16.p, nb * kp * 2));
-        RG_CUDA(cudaMalloc(&s_q16.p, qb_alloc * kp * 2));
-        RG_CUDA(cudaMalloc(&s_max.p, sizeof(float)));
+        RG_WS(s_b16, WS_B16, nb * kp * 2);
+        RG_WS(s_q16, WS_Q16, qb_alloc * kp * 2);
+        RG_WS(s_max, WS_MAX, sizeof(float));
         int rc = knn_tc_convert(B, nb, dim, s_b16.p, nullptr, s);
         if (rc != RG_OK) return rc;
         if ((rc = knn_tc_max_norm(bn, nb, (float *)s_max.p, s)) != RG_OK) return rc;
@@ -480,12 +520,12 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
         rr.metric_l2 = metric_l2;
     }
     const size_t merge_smem = (size_t)sort_n * 8 + (tc ? (size_t)dim * 4 : 0);
-    RG_CUDA(cudaMalloc(&s_top.p, qb_alloc * K * sizeof(unsigned long long)));
-    RG_CUDA(cudaMalloc(&s_cand.p, qb_alloc * cap * sizeof(unsigned long long)));
-    RG_CUDA(cudaMalloc(&s_cnt.p, 2 * qb_alloc * sizeof(uint32_t)));
-    RG_CUDA(cudaMalloc(&s_work.p, (qb_alloc + 1) * sizeof(uint32_t)));
-    RG_CUDA(cudaMalloc(&s_tau.p, qb_alloc * sizeof(float)));
-    RG_CUDA(cudaMalloc(&s_ovf.p, sizeof(uint32_t)));
+    RG_WS(s_top, WS_TOP, qb_alloc * K * sizeof(unsigned long long));
+    RG_WS(s_cand, WS_CAND, qb_alloc * cap * sizeof(unsigned long long));
+    RG_WS(s_cnt, WS_CNT, 2 * qb_alloc * sizeof(uint32_t));
+    RG_WS(s_work, WS_WORK, (qb_alloc + 1) * sizeof(uint32_t));
+    RG_WS(s_tau, WS_TAU, qb_alloc * sizeof(float));
+    RG_WS(s_ovf, WS_OVF, sizeof(uint32_t));
     unsigned long long *top = (unsigned long long *)s_top.p, *cand = (unsigned long long *)s_cand.p;
     uint32_t *cnt = (uint32_t *)s_cnt.p, *ovf = (uint32_t *)s_ovf.p;
     float *tau = (float *)s_tau.p;
@@ -554,6 +594,8 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     RG_CUDA(cudaStreamSynchronize(s));
     return RG_OK;
 }
+
+void knn_release_workspace() { g_ws.release(); }
 
 int topk_merge_device(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
                       float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s) {

@@ -264,20 +264,74 @@ __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchPara
     }
 }
 
+// Same, with the row ring used as two halves of 8 rows (rows_per_batch == 16): the bulk copies of group g + 2 are issued
+// as soon as group g has been read, so eight rows stay in flight while the warp computes distances and inserts — the
+// single-buffered loop above has nothing in flight during that time.  Insertion order is unchanged (groups in order).
+template <bool kL2>
+__device__ __forceinline__ void evaluate_candidates_db(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj) {
+    const int lane = w.lane;
+    const uint32_t row_bytes = p.dim * 4u;
+    const uint32_t rstride = p.row_stride_smem;
+    const int n16 = p.dim >> 4;
+    const bool has8 = (p.dim & 8u) != 0;
+    const int t = lane & 3;
+    const uint32_t ngroups = (n + 7) >> 3;
+    auto issue = [&](uint32_t g) {
+        const uint32_t h = g & 1u;
+        const uint32_t cnt = min(8u, n - 8u * g);
+        if (lane == 0) mbar_expect_tx(w.bar0 + 8u * h, cnt * row_bytes);
+        __syncwarp();
+        if ((uint32_t)lane < cnt) {
+            const uint32_t id = w.cand[8u * g + lane];
+            bulk_g2s(w.rows_u32 + (h * 8u + lane) * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * h);
+        }
+    };
+    issue(0);
+    if (ngroups > 1) issue(1);
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        const uint32_t h = g & 1u;
+        mbar_wait(w.bar0 + 8u * h, (w.phase >> h) & 1u);
+        w.phase ^= (1u << h);
+        const uint32_t r = 8u * g + (lane >> 2);
+        const bool valid = r < n;
+        const float d = row_distance<kL2>(w.rows + (size_t)(h * 8u + (valid ? (lane >> 2) : 0)) * rstride, w.q, n16, has8, t);
+        const uint32_t id = valid ? w.cand[r] : 0u;
+        __syncwarp();  // every lane has read its row: the half may be refilled
+        if (g + 2 < ngroups) issue(g + 2);
+        bool pass = valid && t == 0;
+        if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
+        uint32_t m = __ballot_sync(kFull, pass);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(kFull, d, src);
+            const uint32_t cid = __shfl_sync(kFull, id, src);
+            const bool in = queue_insert(w, p.L, cd, cid);
+            if (in && prefetch_adj) {
+                const char *a = reinterpret_cast<const char *>(p.adj + (size_t)cid * p.adj_stride);
+                const uint32_t bytes = p.adj_stride * 4u;
+                if ((uint32_t)lane * 32u < bytes) prefetch_l2(a + lane * 32u);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <bool kL2>
+__device__ __forceinline__ void evaluate(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj) {
+    if (p.rows_per_batch == 16u) evaluate_candidates_db<kL2>(w, p, n, prefetch_adj);
+    else evaluate_candidates<kL2>(w, p, n, prefetch_adj);
+}
+
 // Visited filter (visited_list_pool.h / src/index_bipartite.cpp:2378-2386): appends the not-yet-visited ids of
 // list[0..cnt) to cand[ncand..] and tags them.  Up to kCandCap ids per call; lists are duplicate-free (deduplicated at upload).
-__device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, uint8_t epoch, const uint32_t *list,
-                                                     uint32_t cnt, uint32_t ncand, uint32_t exclude = 0xffffffffu) {
+__device__ __forceinline__ uint32_t filter_unvisited_ids(WarpCtx &w, uint8_t *tags, uint8_t epoch, const uint32_t (&id)[3],
+                                                         uint32_t cnt, uint32_t ncand, uint32_t exclude) {
     const int lane = w.lane;
-    uint32_t id[3];
     uint8_t tg[3];
     bool valid[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const uint32_t i = j * 32 + lane;
-        valid[j] = i < cnt;
-        id[j] = valid[j] ? __ldg(list + i) : 0u;
-    }
+    for (int j = 0; j < 3; ++j) valid[j] = (uint32_t)(j * 32 + lane) < cnt;
 #pragma unroll
     for (int j = 0; j < 3; ++j) tg[j] = valid[j] ? __ldcg(tags + id[j]) : epoch;
 #pragma unroll
@@ -290,6 +344,16 @@ __device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, 
     }
     __syncwarp();
     return ncand;
+}
+__device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, uint8_t epoch, const uint32_t *list,
+                                                     uint32_t cnt, uint32_t ncand, uint32_t exclude = 0xffffffffu) {
+    uint32_t id[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint32_t i = j * 32 + w.lane;
+        id[j] = i < cnt ? __ldg(list + i) : 0u;
+    }
+    return filter_unvisited_ids(w, tags, epoch, id, cnt, ncand, exclude);
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -333,7 +397,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
     uint8_t *tags = p.tags + (size_t)slot * p.tag_stride;
     uint32_t epoch = p.slot_epoch[slot];
     unsigned long long acc_cmps = 0, acc_hops = 0, acc_adj = 0;
-    const bool prefetch_adj = !kBipartite && p.n_init != 0;  // n_init doubles as the prefetch switch for RoarGraph
+    const bool prefetch_adj = !kBipartite && p.n_init == 1;  // n_init doubles as the prefetch switch for RoarGraph
+    const bool prefetch_next = !kBipartite && p.n_init == 2;
 
     for (;;) {
         uint32_t qidx = 0;
@@ -366,7 +431,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 if (kBuild) __stcg(tags + p.ep, (uint8_t)epoch);  // :1307 the build's search does mark it
             }
             __syncwarp();
-            evaluate_candidates<kL2>(w, p, 1, false);
+            evaluate<kL2>(w, p, 1, false);
         } else {
             for (uint32_t i = lane; i < p.n_init; i += 32) {
                 uint32_t id;
@@ -376,7 +441,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 __stcg(tags + id, (uint8_t)epoch);  // :306 entry points are marked visited
             }
             __syncwarp();
-            evaluate_candidates<kL2>(w, p, p.n_init, false);
+            evaluate<kL2>(w, p, p.n_init, false);
         }
 
         while (w.cur < w.size) {  // has_unexpanded_node
@@ -387,15 +452,42 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 p.exp_dists[(size_t)qidx * p.exp_cap + hops] = ud;
             }
             ++hops;
+            if (prefetch_next && w.cur < w.size) {
+                // unless this hop finds something closer, the node now at `cur` is expanded next: pull its adjacency row
+                // towards L2 while this hop's rows are gathered (3 x 128 B; wrong guesses cost 1 % of a hop's traffic)
+                const char *a = reinterpret_cast<const char *>(p.adj + (size_t)(w.qi[w.cur] & kIdMask) * p.adj_stride);
+                if ((uint32_t)lane * 128u < p.adj_stride * 4u) prefetch_l2(a + lane * 128u);
+            }
             if (!kBipartite) {
+                // the whole fixed-stride adjacency row in ONE round trip: words lane, lane + 32, lane + 64 (word 0 = degree);
+                // a load of the degree followed by a dependent load of the ids would cost two DRAM latencies per hop
                 const uint32_t *arow = p.adj + (size_t)u * p.adj_stride;
-                const uint32_t deg = __ldg(arow);
+                uint32_t wv[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t i = j * 32 + lane;
+                    wv[j] = i < p.adj_stride ? __ldg(arow + i) : 0u;
+                }
+                const uint32_t deg = __shfl_sync(kFull, wv[0], 0);
                 adjw += deg;
-                for (uint32_t off = 0; off < deg; off += kCandCap) {
-                    const uint32_t n = filter_unvisited(w, tags, (uint8_t)epoch, arow + 1 + off, min(deg - off, (uint32_t)kCandCap), 0,
-                                                        kBuild ? p.node_lo + qidx : 0xffffffffu);
+                const uint32_t exclude = kBuild ? p.node_lo + qidx : 0xffffffffu;
+                if (deg < (uint32_t)kCandCap) {
+                    uint32_t nid[3];  // neighbour i = word i + 1: one lane up, lane 31 takes word 0 of the next chunk
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t up = __shfl_sync(kFull, wv[j], (lane + 1) & 31);
+                        const uint32_t nx = __shfl_sync(kFull, wv[j < 2 ? j + 1 : 2], 0);
+                        nid[j] = lane == 31 ? nx : up;
+                    }
+                    const uint32_t n = filter_unvisited_ids(w, tags, (uint8_t)epoch, nid, deg, 0, exclude);
                     cmps += n;
-                    if (n) evaluate_candidates<kL2>(w, p, n, prefetch_adj);
+                    if (n) evaluate<kL2>(w, p, n, prefetch_adj);
+                } else {
+                    for (uint32_t off = 0; off < deg; off += kCandCap) {
+                        const uint32_t n = filter_unvisited(w, tags, (uint8_t)epoch, arow + 1 + off, min(deg - off, (uint32_t)kCandCap), 0, exclude);
+                        cmps += n;
+                        if (n) evaluate<kL2>(w, p, n, prefetch_adj);
+                    }
                 }
             } else {
                 // two-hop expansion through the query nodes (:324-341); hops++ precedes the empty-adjacency skip (:320-323)
@@ -409,7 +501,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                     for (uint64_t off = b2; off < e2; off += 32) {
                         if (ncand + 32 > (uint32_t)kCandCap) {
                             cmps += ncand;
-                            evaluate_candidates<kL2>(w, p, ncand, false);
+                            evaluate<kL2>(w, p, ncand, false);
                             ncand = 0;
                         }
                         ncand = filter_unvisited(w, tags, (uint8_t)epoch, p.csr_nbrs + off, (uint32_t)min((uint64_t)32, e2 - off), ncand);
@@ -417,7 +509,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 }
                 if (ncand) {
                     cmps += ncand;
-                    evaluate_candidates<kL2>(w, p, ncand, false);
+                    evaluate<kL2>(w, p, ncand, false);
                 }
             }
         }

@@ -19,16 +19,20 @@ def shard_range(nb: int, shard: int, n_shards: int):
     return shard * nb // n_shards, (shard + 1) * nb // n_shards
 
 
-def gather_topk(local_dists, local_ids, group=None):
-    """all-gather [nq, k] per-shard lists into [G, nq, k] tensors (same device/backend as the inputs)."""
+def gather_topk(local_dists, local_ids, group=None, out=None):
+    """all-gather [nq, k] per-shard lists into [G, nq, k] tensors (same device/backend as the inputs).
+    `out` = optional (dists [G*nq, k], ids [G*nq, k]) buffers to gather into."""
     import torch
     import torch.distributed as dist
 
     G = dist.get_world_size(group)
     nq, k = local_dists.shape
     # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [G][nq][k]
-    out_d = torch.empty((G * nq, k), dtype=local_dists.dtype, device=local_dists.device)
-    out_i = torch.empty((G * nq, k), dtype=local_ids.dtype, device=local_ids.device)
+    if out is not None:
+        out_d, out_i = out
+    else:
+        out_d = torch.empty((G * nq, k), dtype=local_dists.dtype, device=local_dists.device)
+        out_i = torch.empty((G * nq, k), dtype=local_ids.dtype, device=local_ids.device)
     dist.all_gather_into_tensor(out_d, local_dists.contiguous(), group=group)
     dist.all_gather_into_tensor(out_i, local_ids.contiguous(), group=group)
     return out_d.view(G, nq, k), out_i.view(G, nq, k)
@@ -52,8 +56,11 @@ class ShardedRoarIndex:
 
         key = (nq, k)
         if key not in self._buf:
+            G = self.world
             self._buf[key] = (torch.empty((nq, k), dtype=torch.int32, device=device),
-                              torch.empty((nq, k), dtype=torch.float32, device=device))
+                              torch.empty((nq, k), dtype=torch.float32, device=device),
+                              torch.empty((G * nq, k), dtype=torch.float32, device=device),
+                              torch.empty((G * nq, k), dtype=torch.int32, device=device))
         return self._buf[key]
 
     def search_dev(self, d_q, k: int, L_pq: int, out_ids, out_dists, d_cmps=None, d_hops=None) -> int:
@@ -67,28 +74,42 @@ class ShardedRoarIndex:
                 out_ids.add_(self.row_lo)
                 return 2
             return 1
-        loc_i, loc_d = self._scratch(d_q.shape[0], k, d_q.device)
+        loc_i, loc_d, g_d, g_i = self._scratch(d_q.shape[0], k, d_q.device)
         self.index.search_dev(d_q, k, L_pq, loc_i, loc_d, d_cmps, d_hops, stream=stream)
         loc_i.add_(self.row_lo)  # local -> global ids, like start_id in compute_groundtruth.cpp:413
-        all_d, all_i = gather_topk(loc_d, loc_i, self.group)
+        all_d, all_i = gather_topk(loc_d, loc_i, self.group, out=(g_d, g_i))
         rg.topk_merge_dev(all_d, all_i, out_dists, out_ids, stream=stream)
         return 3
 
+    def _e2e_buffers(self, nq, dim, k, device):
+        import torch
+
+        key = ("e2e", nq, dim, k)
+        if key not in self._buf:
+            self._buf[key] = dict(
+                d_q=torch.empty((nq, dim), dtype=torch.float32, device=device),
+                d_i=torch.empty((nq, k), dtype=torch.int32, device=device),
+                d_d=torch.empty((nq, k), dtype=torch.float32, device=device),
+                h_i=torch.empty((nq, k), dtype=torch.int32).pin_memory(),
+                h_d=torch.empty((nq, k), dtype=torch.float32).pin_memory())
+        return self._buf[key]
+
     def search(self, queries: np.ndarray, k: int, L_pq: int):
-        """Host buffers in (ideally pinned), host numpy out: H2D, per-shard search, all-gather, merge, D2H."""
+        """Host buffers in (ideally pinned), host numpy out: H2D, per-shard search, all-gather, merge, D2H.  All device
+        and pinned staging buffers are cached per shape, every copy is asynchronous on torch's current stream and the
+        call synchronises once."""
         import torch
 
         dev = torch.device("cuda", torch.cuda.current_device())
         q = torch.from_numpy(queries)
-        d_q = q.to(dev, non_blocking=True)
-        nq = d_q.shape[0]
-        out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        self.search_dev(d_q, k, L_pq, out_i, out_d)
-        ids = out_i.cpu().numpy().view(np.uint32)
-        dists = out_d.cpu().numpy()
-        self.index.check(torch.cuda.current_stream())
-        return ids, dists
+        nq, dim = q.shape
+        b = self._e2e_buffers(nq, dim, k, dev)
+        b["d_q"].copy_(q, non_blocking=True)
+        self.search_dev(b["d_q"], k, L_pq, b["d_i"], b["d_d"])
+        b["h_i"].copy_(b["d_i"], non_blocking=True)
+        b["h_d"].copy_(b["d_d"], non_blocking=True)
+        self.index.check(torch.cuda.current_stream())  # synchronises the stream, raises the reference's errors
+        return b["h_i"].numpy().view(np.uint32), b["h_d"].numpy()
 
 
 def sharded_knn_dev(d_base_shard, d_queries, K: int, metric, row_lo: int, group=None, batch: int = 1 << 20,

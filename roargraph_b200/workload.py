@@ -158,6 +158,7 @@ def build_search_workload(nb: int, dim: int, metric: str, ntrain: int, nq: int, 
             os.replace(tmp, cpath)
     w.d_train_sample = train[:min(ntrain, 151552)].clone()
     del train
+    rg.knn_release_workspace()  # the kNN scratch (bf16 base copy, candidate lists) is not needed while searching
     torch.cuda.empty_cache()
     g = w.index.graph_size()
     w.info.update(nd_local=nd, avg_degree=round(g["nnz"] / nd, 2), max_degree=g["max_degree"], ep=g["ep"])

@@ -21,7 +21,7 @@ s = torch.cuda.current_stream()
 ref = {}
 print("L,R,ctas,warps,prefetch,grid,smem,ms,qps,GBps,frac")
 for L in Ls:
-    for R, C, Wp, P in itertools.product((8, 16, 24), (3, 4, 6, 8), (4,), (1, 0)):
+    for R, C, Wp, P in itertools.product((8, 16), (2, 3, 4, 6, 7, 8), (2, 4), (0,)):
         os.environ.update(RG_ROWS_PER_BATCH=str(R), RG_CTAS_PER_SM=str(C), RG_WARPS_PER_CTA=str(Wp), RG_PREFETCH_ADJ=str(P))
         ts = []
         for rep in range(4):
