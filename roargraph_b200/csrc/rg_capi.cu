@@ -82,6 +82,17 @@ int rg::ensure_tags(rg_index *idx, uint32_t slots) {
     return RG_OK;
 }
 
+int rg::ensure_vtab(rg_index *idx, uint64_t words) {
+    if (words <= idx->vtab_words) return RG_OK;
+    if (idx->d_vtab) cudaFree(idx->d_vtab);
+    idx->d_vtab = nullptr;
+    idx->vtab_words = 0;
+    RG_CUDA(cudaMalloc(&idx->d_vtab, words * sizeof(uint32_t)));
+    RG_CUDA(cudaMemset(idx->d_vtab, 0xff, words * sizeof(uint32_t)));
+    idx->vtab_words = words;
+    return RG_OK;
+}
+
 // Number of query slots (resident warps) whose tag arrays fit in a bounded share of free HBM.
 uint32_t rg::affordable_slots(rg_index *idx) {
     size_t free_b = 0, total_b = 0;
@@ -258,6 +269,7 @@ int rg_index_destroy(rg_index *idx) {
     if (idx->d_row_off) cudaFree(idx->d_row_off);
     if (idx->d_csr) cudaFree(idx->d_csr);
     if (idx->d_tags) cudaFree(idx->d_tags);
+    if (idx->d_vtab) cudaFree(idx->d_vtab);
     if (idx->d_slot_epoch) cudaFree(idx->d_slot_epoch);
     if (idx->d_counter) cudaFree(idx->d_counter);
     if (idx->d_stats) cudaFree(idx->d_stats);
@@ -360,6 +372,42 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
     if (rc != RG_OK) return rc;
     p.tags = idx->d_tags;
     p.slot_epoch = idx->d_slot_epoch;
+    p.vtab = nullptr;
+    p.vt_words = 0;
+    if (!bipartite) {
+        // Visited set of SearchRoarGraph: a per-slot hash table small enough for all slots' tables to stay in L2, so the
+        // visited checks stop costing DRAM transactions (the byte-per-node tag array costs one random 32-byte DRAM read and
+        // one write-back per examined neighbour: ~25 % of the kernel's DRAM transactions).  Exact: 16-bit entries hold the
+        // low bits of a bijective hash of the id, the bucket index holds the rest.  Tables that would not fit the L2
+        // budget (large L_pq) fall back to the tag arrays; so does a query whose bucket pair overflows, mid-flight.
+        const char *vm = getenv("RG_VISITED");  // "hash" opts in; default = the tag arrays (the table's extra L2 round trips
+        const bool force_tags = !vm || vm[0] != 'h', force_hash = vm && vm[0] == 'h';  // cost more than its DRAM savings, r1 tune)
+        const char *mb = getenv("RG_VTAB_MB");
+        const uint64_t budget = (mb ? strtoull(mb, nullptr, 10) : 64ull) << 20;
+        uint32_t bits = 1;
+        while (bits < 31 && (1ull << bits) < idx->nd) ++bits;
+        const uint64_t want_entries = (uint64_t)(48.0 * L + 256.0) * 5 / 4;  // ~1.25 x the expected distance evaluations
+        uint32_t bbits = 0;
+        while ((16ull << bbits) < want_entries) ++bbits;
+        if (const char *fb = getenv("RG_VTAB_BBITS")) bbits = (uint32_t)strtoul(fb, nullptr, 10);  // test hook: tiny tables overflow
+        if (bits > bbits + 14) bbits = bits - 14;  // the remainder must fit 14 bits
+        if (bbits > bits) bbits = bits;
+        const uint64_t words = 8ull << bbits;
+        const uint64_t slots = (uint64_t)l.grid * l.warps_per_cta;
+        if (!force_tags && (force_hash || slots * words * 4 <= budget) && words * 4 <= (64u << 20)) {
+            rc = ensure_vtab(idx, slots * words);
+            if (rc != RG_OK) return rc;
+            p.vtab = idx->d_vtab;
+            p.vt_words = (uint32_t)words;
+            p.vt_bbits = bbits;
+            p.vt_rbits = bits - bbits;
+            p.vt_mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+            p.vt_mul = 0x9E3779B1u;  // odd: id -> id * mul mod 2^bits is a bijection
+            uint32_t inv = p.vt_mul;  // Newton iteration for the inverse modulo 2^32
+            for (int it = 0; it < 5; ++it) inv *= 2u - p.vt_mul * inv;
+            p.vt_mulinv = inv;
+        }
+    }
     idx->last_launch = l;
     return bipartite ? launch_bipartite(p, l, s) : launch_roargraph(p, l, s);
 }

@@ -50,10 +50,15 @@ struct SearchParams {
     uint32_t row_stride_smem; // floats; == dim padded so that (stride % 32) == 16 (bank-conflict-free float4 reads)
     uint32_t warp_smem_bytes; // bytes of dynamic smem per warp
     int metric_l2;            // 1: squared L2, 0: negative inner product
+    // L2-resident exact visited set (SearchRoarGraph only; see rg_search.cu "visited table"): per slot 2^vt_bbits buckets
+    // of 16 x 16-bit entries; 0 = use the tag arrays
+    uint32_t *vtab;           // n_slots x vt_words
+    uint32_t vt_words;        // 32-bit words per slot (8 per bucket)
+    uint32_t vt_bbits, vt_rbits, vt_mask, vt_mul, vt_mulinv;
 };
 
 struct SearchLaunch {
-    uint32_t grid, block, smem_bytes, rows_per_batch, warps_per_cta, ctas_per_sm;
+    uint32_t grid, block, smem_bytes, rows_per_batch, warps_per_cta, ctas_per_sm, warps_per_sm;
 };
 
 // Computes the launch geometry (and per-warp smem layout fields of `p`) for queue length L.
@@ -105,6 +110,8 @@ struct rg_index {
     uint32_t *d_slot_epoch = nullptr;
     uint32_t n_slots = 0;
     uint64_t tag_stride = 0;
+    uint32_t *d_vtab = nullptr;  // hashed visited tables (n_vt_slots x vt_words), all-ones = empty
+    uint64_t vtab_words = 0;
     // per-call scratch
     uint32_t *d_counter = nullptr;
     unsigned long long *d_stats = nullptr;
@@ -119,6 +126,7 @@ namespace rg {
 int sm_count();
 int ensure_device_ready();
 int ensure_tags(rg_index *idx, uint32_t slots);
+int ensure_vtab(rg_index *idx, uint64_t words);
 uint32_t affordable_slots(rg_index *idx);
 
 // tensor-core candidate filter of the kNN (rg_knn_tc.cu)

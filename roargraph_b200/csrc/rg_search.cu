@@ -15,6 +15,7 @@
 //   * distances reproduce the reference's AVX-512 rounding order exactly (distance.h:39-89,179-225 as compiled):
 //     4 lanes per row, each owning 4 of the 16 virtual SIMD lanes; unfused mul+add in the 16-wide loop,
 //     fma in the 8-wide tail, pairwise folds by shuffles.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -51,6 +52,29 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// One row through the bulk-copy engine with an L2 eviction policy (rows are streamed once: evict-first keeps them from
+// pushing the visited tables out of L2).
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 32-byte bucket of the visited table, kept in L2 with evict-last priority (256-bit load / store, sm_100)
+__device__ __forceinline__ void ld_bucket(const uint32_t *p, uint32_t (&v)[8]) {
+    asm volatile("ld.relaxed.gpu.global.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_bucket_empty(uint32_t *p) {
+    const uint32_t x = 0xffffffffu;
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(x) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -125,6 +149,7 @@ struct WarpCtx {
     uint32_t bar0;     // shared address of mbarrier[0] (4 barriers, one per group of 8 rows)
     uint32_t rows_u32; // shared address of rows
     uint32_t size, cur, phase;
+    uint64_t row_policy;  // L2 eviction policy of the row copies (0 = none)
     int lane;
 };
 
@@ -233,7 +258,8 @@ __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchPara
         if ((uint32_t)lane < ngroups) mbar_expect_tx(w.bar0 + 8u * lane, min(8u, nb - 8u * lane) * row_bytes);
         if ((uint32_t)lane < nb) {
             const uint32_t id = w.cand[b0 + lane];
-            bulk_g2s(w.rows_u32 + lane * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * (lane >> 3));
+            if (w.row_policy) bulk_g2s_hint(w.rows_u32 + lane * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * (lane >> 3), w.row_policy);
+            else bulk_g2s(w.rows_u32 + lane * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * (lane >> 3));
         }
         for (uint32_t g = 0; g < ngroups; ++g) {
             mbar_wait(w.bar0 + 8u * g, (w.phase >> g) & 1u);
@@ -283,7 +309,8 @@ __device__ __forceinline__ void evaluate_candidates_db(WarpCtx &w, const SearchP
         __syncwarp();
         if ((uint32_t)lane < cnt) {
             const uint32_t id = w.cand[8u * g + lane];
-            bulk_g2s(w.rows_u32 + (h * 8u + lane) * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * h);
+            if (w.row_policy) bulk_g2s_hint(w.rows_u32 + (h * 8u + lane) * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * h, w.row_policy);
+            else bulk_g2s(w.rows_u32 + (h * 8u + lane) * rstride * 4u, p.base + (size_t)id * p.dim, row_bytes, w.bar0 + 8u * h);
         }
     };
     issue(0);
@@ -356,6 +383,99 @@ __device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, 
     return filter_unvisited_ids(w, tags, epoch, id, cnt, ncand, exclude);
 }
 
+// ---- visited table --------------------------------------------------------------------------------------------------------
+// Exact visited set of one query in 2^bbits buckets of 16 x 16-bit entries (one 32-byte sector per bucket).  With
+// h = (id * mul) mod 2^bits (a bijection, mul odd) the bucket is the top bbits of h and the entry stores the low rbits
+// (<= 14) — bucket index + entry identify the id, so membership is exact.  Bit 14 of an entry marks an id whose home
+// bucket was full when it arrived and that lives in the next bucket instead; 0xffff = empty.  Lookup: found in the home
+// bucket -> visited; home bucket has an empty entry -> not visited (entries are never removed, so nothing was ever displaced
+// from a non-full bucket) -> insert; home full -> same test on the next bucket with the displaced pattern; both full ->
+// the query migrates to the tag array (vt_migrate) and continues there.
+// Returns 0 = already visited, 1 = fresh and recorded, 2 = bucket full.
+__device__ __forceinline__ int vt_bucket_insert(uint32_t *bucket, uint32_t (&w)[8], uint32_t pat) {
+    const uint32_t pat2 = pat | (pat << 16);
+    uint32_t hit = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hit |= __vcmpeq2(w[i], pat2);
+    if (hit) return 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        for (;;) {
+            const bool lo_empty = (w[i] & 0xffffu) == 0xffffu, hi_empty = (w[i] >> 16) == 0xffffu;
+            if (!lo_empty && !hi_empty) break;
+            const uint32_t desired = lo_empty ? ((w[i] & 0xffff0000u) | pat) : ((w[i] & 0x0000ffffu) | (pat << 16));
+            const uint32_t old = atomicCAS(bucket + i, w[i], desired);
+            if (old == w[i]) return 1;
+            w[i] = old;  // another lane of this warp filled a half of this word (a different id: lists are duplicate-free)
+        }
+    }
+    return 2;
+}
+
+// Visited filter on the table: same contract as filter_unvisited_ids; *overflow is set (warp-uniform) when some lane could
+// not record a fresh id (ovf_ids[j] != 0xffffffff names them).
+__device__ __forceinline__ uint32_t filter_unvisited_vt(WarpCtx &w, const SearchParams &p, uint32_t *vt, const uint32_t (&id)[3],
+                                                        uint32_t cnt, uint32_t ncand, uint32_t (&ovf_ids)[3], bool *overflow) {
+    const int lane = w.lane;
+    const uint32_t nb_mask = (1u << p.vt_bbits) - 1u, rmask = (1u << p.vt_rbits) - 1u;
+    bool valid[3];
+    uint32_t bkt[3], rem[3];
+    uint32_t wb[3][8];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        valid[j] = (uint32_t)(j * 32 + lane) < cnt;
+        const uint32_t h = (id[j] * p.vt_mul) & p.vt_mask;
+        bkt[j] = h >> p.vt_rbits;
+        rem[j] = h & rmask;
+        ovf_ids[j] = 0xffffffffu;
+        if (valid[j]) ld_bucket(vt + (size_t)bkt[j] * 8u, wb[j]);
+    }
+    bool any_ovf = false;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        bool fresh = false;
+        if (valid[j]) {
+            int r = vt_bucket_insert(vt + (size_t)bkt[j] * 8u, wb[j], rem[j]);
+            if (r == 2) {
+                const uint32_t nb = (bkt[j] + 1u) & nb_mask;
+                uint32_t wn[8];
+                ld_bucket(vt + (size_t)nb * 8u, wn);
+                r = vt_bucket_insert(vt + (size_t)nb * 8u, wn, rem[j] | 0x4000u);
+                if (r == 2) {
+                    ovf_ids[j] = id[j];  // fresh (in neither bucket) but not recorded
+                    any_ovf = true;
+                }
+            }
+            fresh = r != 0;
+        }
+        const uint32_t m = __ballot_sync(kFull, fresh);
+        if (fresh) w.cand[ncand + __popc(m & ((1u << lane) - 1u))] = id[j];
+        ncand += __popc(m);
+    }
+    *overflow = __any_sync(kFull, any_ovf);
+    __syncwarp();
+    return ncand;
+}
+
+// The table is (nearly) full: mark every recorded id in the tag array and carry on with tags for the rest of the query.
+__device__ __forceinline__ void vt_migrate(const SearchParams &p, const uint32_t *vt, uint8_t *tags, uint8_t epoch, int lane) {
+    const uint32_t nbuckets = 1u << p.vt_bbits, nb_mask = nbuckets - 1u, rmask = (1u << p.vt_rbits) - 1u;
+    for (uint32_t b = lane; b < nbuckets; b += 32) {
+        uint32_t wv[8];
+        ld_bucket(vt + (size_t)b * 8u, wv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t e = (i & 1) ? (wv[i >> 1] >> 16) : (wv[i >> 1] & 0xffffu);
+            if (e == 0xffffu) continue;
+            const uint32_t home = (e & 0x4000u) ? ((b - 1u) & nb_mask) : b;
+            const uint32_t h = (home << p.vt_rbits) | (e & rmask);
+            const uint32_t id = (h * p.vt_mulinv) & p.vt_mask;
+            __stcg(tags + id, epoch);
+        }
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -367,7 +487,9 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 // connectivity-enhancement search, src/index_bipartite.cpp:1279-1350: the query is base row node_lo + ticket, that node
 // is never evaluated, the entry point IS marked visited, and the expanded nodes are the output).
 // kMinBlocks: resident CTAs per SM the register allocation is capped for (4 -> 104 regs, 6 -> 80, 8 -> 64; no spills).
-template <bool kL2, int kMode, int kMinBlocks>
+// kVt: the visited set is the hashed table (SearchRoarGraph only); compiled separately so that the tag-array kernels do not
+// carry its registers.
+template <bool kL2, int kMode, int kMinBlocks, bool kVt>
 __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const SearchParams p) {
     constexpr bool kBipartite = kMode == 1;
     constexpr bool kBuild = kMode == 2;
@@ -396,6 +518,18 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
     const uint32_t slot = blockIdx.x * warps_per_cta + warp;
     uint8_t *tags = p.tags + (size_t)slot * p.tag_stride;
     uint32_t epoch = p.slot_epoch[slot];
+    constexpr bool use_vt = kVt && kMode == 0;  // hashed visited table (SearchRoarGraph), else the tag array
+    uint32_t *vt = use_vt ? p.vtab + (size_t)slot * p.vt_words : nullptr;
+    w.row_policy = use_vt ? policy_evict_first() : 0ull;
+    // VisitedList::reset (visited_list_pool.h:20-26): bump the tag, clear the array when it wraps
+    auto next_epoch = [&]() {
+        if (++epoch > 255u) {
+            uint4 z = make_uint4(0, 0, 0, 0);
+            for (uint64_t i = (uint64_t)lane * 16u; i < p.tag_stride; i += 512u) *reinterpret_cast<uint4 *>(tags + i) = z;
+            epoch = 1;
+            __threadfence_block();
+        }
+    };
     unsigned long long acc_cmps = 0, acc_hops = 0, acc_adj = 0;
     const bool prefetch_adj = !kBipartite && p.n_init == 1;  // n_init doubles as the prefetch switch for RoarGraph
     const bool prefetch_next = !kBipartite && p.n_init == 2;
@@ -406,13 +540,31 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
         qidx = __shfl_sync(kFull, qidx, 0);
         if (qidx >= p.nq) break;
 
-        // VisitedList::reset (visited_list_pool.h:20-26): bump the tag, clear the array when it wraps
-        if (++epoch > 255u) {
-            uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint64_t i = (uint64_t)lane * 16u; i < p.tag_stride; i += 512u) *reinterpret_cast<uint4 *>(tags + i) = z;
-            epoch = 1;
-            __threadfence_block();
+        bool on_tags = !use_vt;  // a query starts on the table and migrates to the tags only if a bucket pair overflows
+        if (use_vt) {
+            for (uint32_t i = (uint32_t)lane * 8u; i < p.vt_words; i += 256u) st_bucket_empty(vt + i);
+            __syncwarp();
+        } else {
+            next_epoch();
         }
+        // visited filter of up to 96 ids held 3 per lane: table or tags
+        auto visit = [&](const uint32_t (&vid)[3], uint32_t vcnt, uint32_t exclude) -> uint32_t {
+            if (!use_vt || on_tags) return filter_unvisited_ids(w, tags, (uint8_t)epoch, vid, vcnt, 0, exclude);
+            uint32_t ovf_ids[3];
+            bool ovf;
+            const uint32_t n = filter_unvisited_vt(w, p, vt, vid, vcnt, 0, ovf_ids, &ovf);
+            if (ovf) {
+                next_epoch();
+                __syncwarp();
+                vt_migrate(p, vt, tags, (uint8_t)epoch, lane);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (ovf_ids[j] != 0xffffffffu) __stcg(tags + ovf_ids[j], (uint8_t)epoch);
+                __syncwarp();
+                on_tags = true;
+            }
+            return n;
+        };
         {
             const float4 *src = reinterpret_cast<const float4 *>(
                 kBuild ? p.base + (size_t)(p.node_lo + qidx) * p.dim : p.queries + (size_t)qidx * p.dim);
@@ -479,12 +631,16 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                         const uint32_t nx = __shfl_sync(kFull, wv[j < 2 ? j + 1 : 2], 0);
                         nid[j] = lane == 31 ? nx : up;
                     }
-                    const uint32_t n = filter_unvisited_ids(w, tags, (uint8_t)epoch, nid, deg, 0, exclude);
+                    const uint32_t n = visit(nid, deg, exclude);
                     cmps += n;
                     if (n) evaluate<kL2>(w, p, n, prefetch_adj);
                 } else {
                     for (uint32_t off = 0; off < deg; off += kCandCap) {
-                        const uint32_t n = filter_unvisited(w, tags, (uint8_t)epoch, arow + 1 + off, min(deg - off, (uint32_t)kCandCap), 0, exclude);
+                        const uint32_t c = min(deg - off, (uint32_t)kCandCap);
+                        uint32_t nid[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) nid[j] = (uint32_t)(j * 32 + lane) < c ? __ldg(arow + 1 + off + j * 32 + lane) : 0u;
+                        const uint32_t n = visit(nid, c, exclude);
                         cmps += n;
                         if (n) evaluate<kL2>(w, p, n, prefetch_adj);
                     }
@@ -544,6 +700,36 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
     }
 }
 
+// Visited-tag maintenance before a launch: a slot whose 8-bit epoch could wrap during the coming launch gets its tag array
+// cleared here by a whole grid (a 10 MB clear by the one warp that owns the slot takes tens of milliseconds under load and
+// stalls the launch; the in-kernel clear remains as the fallback for a slot that still overruns).
+constexpr uint64_t kClearChunk = 1ull << 20;
+__global__ void tags_clear_kernel(uint8_t *tags, const uint32_t *slot_epoch, uint64_t tag_stride, uint32_t thr) {
+    const uint32_t slot = blockIdx.y;
+    if (slot_epoch[slot] < thr) return;
+    const uint64_t off = (uint64_t)blockIdx.x * kClearChunk;
+    if (off >= tag_stride) return;
+    const uint64_t n16 = (min(kClearChunk, tag_stride - off)) >> 4;  // tag_stride is a multiple of 16
+    uint4 *dst = reinterpret_cast<uint4 *>(tags + (size_t)slot * tag_stride + off);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = z;
+}
+__global__ void tags_reset_kernel(uint32_t *slot_epoch, uint32_t n_slots, uint32_t thr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots && slot_epoch[i] >= thr) slot_epoch[i] = 0;
+}
+int maintain_tags(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
+    const uint32_t slots = l.grid * l.warps_per_cta;
+    const uint32_t per_slot = (p.nq + slots - 1) / slots;
+    const uint32_t margin = std::min<uint32_t>(200u, 4u * per_slot + 8u);
+    const uint32_t thr = 255u - margin;
+    dim3 grid((unsigned)((p.tag_stride + kClearChunk - 1) / kClearChunk), slots);
+    tags_clear_kernel<<<grid, 256, 0, s>>>(p.tags, p.slot_epoch, p.tag_stride, thr);
+    tags_reset_kernel<<<(slots + 255) / 256, 256, 0, s>>>(p.slot_epoch, slots, thr);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
 uint32_t env_u32(const char *name, uint32_t dflt) {
     const char *v = getenv(name);
     if (!v || !*v) return dflt;
@@ -557,12 +743,14 @@ uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L)
     return (b + 127u) & ~127u;
 }
 
-template <bool kL2, int kMode, int kMinBlocks>
+template <bool kL2, int kMode, int kMinBlocks, bool kVt = false>
 int launch_v(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
-    auto kern = beam_search_kernel<kL2, kMode, kMinBlocks>;
+    auto kern = beam_search_kernel<kL2, kMode, kMinBlocks, kVt>;
     RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
     RG_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), s));
     RG_CUDA(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s));
+    int rc = maintain_tags(p, l, s);
+    if (rc != RG_OK) return rc;
     kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
     RG_CUDA(cudaGetLastError());
     return RG_OK;
@@ -570,9 +758,10 @@ int launch_v(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
 
 template <bool kL2, int kMode>
 int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
-    if (l.ctas_per_sm > 6) return launch_v<kL2, kMode, 8>(p, l, s);
-    if (l.ctas_per_sm > 4) return launch_v<kL2, kMode, 6>(p, l, s);
-    return launch_v<kL2, kMode, 4>(p, l, s);
+    if (kMode == 0 && p.vtab) return launch_v<kL2, 0, 4, true>(p, l, s);  // needs the 4-CTA register budget (plan_search caps it)
+    if (l.warps_per_sm > 24) return launch_v<kL2, kMode, 8>(p, l, s);  // 64 registers
+    if (l.warps_per_sm > 16) return launch_v<kL2, kMode, 6>(p, l, s);  // 80
+    return launch_v<kL2, kMode, 4>(p, l, s);                           // up to 127
 }
 
 }  // namespace
@@ -586,24 +775,37 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     if (R < 8) R = 8;
     if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
     R &= ~7u;
-    uint32_t warps = env_u32("RG_WARPS_PER_CTA", 4);
-    if (warps < 1) warps = 1;
-    if (warps > 4) warps = 4;
     uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
-    while (warps * wb > kMaxSmemPerCta && R > 8) {
+    while (wb > kMaxSmemPerCta && R > 8) {
         R -= 8;
         wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
     }
-    while (warps > 1 && warps * wb > kMaxSmemPerCta) warps >>= 1;
-    if (warps * wb > kMaxSmemPerCta) {
+    if (wb > kMaxSmemPerCta) {
         set_error("L_pq / dim too large for one warp's shared-memory working set");
         return RG_EINVAL;
     }
-    uint32_t ctas = kMaxSmemPerCta / (warps * wb + 1024u);
-    if (ctas < 1) ctas = 1;
-    const uint32_t max_ctas = (warps == 4) ? 8u : 16u / warps;  // 8 x 128 threads x 64 registers fill the register file
-    if (ctas > max_ctas) ctas = max_ctas;
-    if (ctas == 7) ctas = 6;  // register variants exist for 4, 6 and 8 resident CTAs
+    // Warps per CTA: 4 unless a finer CTA granularity keeps more warps resident (long queues: the per-warp working set
+    // grows with L_pq, and whole 4-warp CTAs then waste up to a third of the shared memory).  At most 32 warps per SM
+    // (64 registers per thread), at most 32 CTAs per SM.
+    uint32_t warps = 4, ctas = 0;
+    const uint32_t env_warps = env_u32("RG_WARPS_PER_CTA", 0);
+    uint32_t best_total = 0;
+    for (uint32_t wc = 4; wc >= 1; wc >>= 1) {
+        if (env_warps && wc != env_warps) continue;
+        if (wc * wb > kMaxSmemPerCta) continue;
+        uint32_t c = kMaxSmemPerCta / (wc * wb + 1024u);
+        c = std::min(c, 32u / wc);
+        const uint32_t total = c * wc;
+        if (total > best_total + (best_total >> 3)) {  // a finer granularity must buy > 12 % more resident warps
+            best_total = total;
+            warps = wc;
+            ctas = c;
+        }
+    }
+    if (ctas < 1) {
+        warps = 1;
+        ctas = 1;
+    }
     const uint32_t env_ctas = env_u32("RG_CTAS_PER_SM", 0);
     if (env_ctas && env_ctas < ctas) ctas = env_ctas;
     uint32_t grid = (uint32_t)sm_count * ctas;
@@ -619,6 +821,7 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     l.rows_per_batch = R;
     l.warps_per_cta = warps;
     l.ctas_per_sm = ctas;
+    l.warps_per_sm = ctas * warps;
     return RG_OK;
 }
 

@@ -19,10 +19,10 @@ d_c = torch.empty(nq, dtype=torch.int32, device=dev); d_h = torch.empty(nq, dtyp
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 s = torch.cuda.current_stream()
 ref = {}
-print("L,R,ctas,warps,prefetch,grid,smem,ms,qps,GBps,frac")
+print("L,R,ctas,warps,prefetch,visited,grid,smem,ms,qps,GBps,frac")
 for L in Ls:
-    for R, C, Wp, P in itertools.product((8, 16), (2, 3, 4, 6, 7, 8), (2, 4), (0,)):
-        os.environ.update(RG_ROWS_PER_BATCH=str(R), RG_CTAS_PER_SM=str(C), RG_WARPS_PER_CTA=str(Wp), RG_PREFETCH_ADJ=str(P))
+    for R, C, Wp, P, V in itertools.product((8, 16), (3, 4, 6), (4,), (0, 2), ("tags", "hash")):
+        os.environ.update(RG_ROWS_PER_BATCH=str(R), RG_CTAS_PER_SM=str(C), RG_WARPS_PER_CTA=str(Wp), RG_PREFETCH_ADJ=str(P), RG_VISITED=V, RG_VTAB_MB="512")
         ts = []
         for rep in range(4):
             flush.fill_(rep)
@@ -34,4 +34,4 @@ for L in Ls:
         assert (ids == ref[L]).all(), "results changed with the launch geometry"
         st, ll = w.index.last_stats(), w.index.last_launch()
         ms = min(ts[1:]); gb = ((st["cmps"] + nq) * 800 + st["adj_words"] * 4) / ms / 1e6
-        print(f"{L},{R},{C},{Wp},{P},{ll['grid']},{ll['smem_bytes']},{ms:.3f},{nq / ms * 1e3:.0f},{gb:.0f},{gb / 6547.5:.3f}", flush=True)
+        print(f"{L},{R},{C},{Wp},{P},{V},{ll['grid']},{ll['smem_bytes']},{ms:.3f},{nq / ms * 1e3:.0f},{gb:.0f},{gb / 6547.5:.3f}", flush=True)

@@ -18,7 +18,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128, 6) gather(const float *base, uint32_t row_floats, const uint32_t *ids, uint32_t n_ids, float *out) {
+__global__ void __launch_bounds__(128, 6) gather(const float *base, uint32_t row_floats, const uint32_t *ids, uint32_t n_ids, float *out,
+                                                 uint8_t *tags, uint64_t tag_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rstride = row_floats + 16;  // floats
@@ -34,7 +35,14 @@ __global__ void __launch_bounds__(128, 6) gather(const float *base, uint32_t row
     float acc = 0.f;
     uint32_t phase = 0;
     for (uint32_t i0 = gw * 8; i0 + 8 <= n_ids; i0 += nwarps * 8) {
-        if (MODE == 0) {
+        if (MODE == 3) {
+            // the search kernel's visited-tag traffic: ~10 random 1-byte reads and 8 random 1-byte writes per 8 rows
+            const uint64_t h = ((uint64_t)ids[i0 + (lane & 7)] * 0x9E3779B97F4A7C15ull + lane * 0xBF58476D1CE4E5B9ull) % tag_bytes;
+            uint8_t t = 0;
+            if (lane < 10) t = __ldcg(tags + h);
+            if (lane < 8 && t != 77) __stcg(tags + h, (uint8_t)77);
+        }
+        if (MODE == 0 || MODE == 3) {
             if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_u), "r"(8 * row_bytes) : "memory");
             __syncwarp();
             if (lane < 8) {
@@ -94,16 +102,22 @@ int main(int argc, char **argv) {
     cudaFuncSetAttribute(gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    uint8_t *tags;
+    const uint64_t tag_bytes = 20ull << 30;
+    cudaMalloc(&tags, tag_bytes);
+    cudaMemset(tags, 0, tag_bytes);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const char *names[3] = {"cp.async.bulk", "ldg.128", "cp.async.cg 16B"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char *names[4] = {"cp.async.bulk", "ldg.128", "cp.async.cg 16B", "bulk + tag bytes"};
+    for (int mode = 0; mode < 4; ++mode) {
         for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(e0);
-            if (mode == 0) gather<0><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out);
-            if (mode == 1) gather<1><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out);
-            if (mode == 2) gather<2><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out);
+            if (mode == 0) gather<0><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out, tags, tag_bytes);
+            if (mode == 1) gather<1><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out, tags, tag_bytes);
+            if (mode == 3) gather<3><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out, tags, tag_bytes);
+            if (mode == 2) gather<2><<<148 * 6, 128, smem>>>(base, row_floats, ids, n_ids, out, tags, tag_bytes);
             cudaEventRecord(e1);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("%s: %s\n", names[mode], cudaGetErrorString(e)); return 1; }
