@@ -455,8 +455,9 @@ def main():
                        "avg_cmps": st["cmps"] / nq, "avg_hops": st["hops"] / nq, "launch": ll, "setup": w.info},
             "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(np.mean(e2e_ms))},
+                    "ms_per_step": float(np.mean(e2e_ms)), "step_ms": [round(float(x), 3) for x in e2e_ms]},
             "gpu_launches": int(launches),
+            "step_ms": [round(float(x), 3) for x in step_ms],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "beam_search_kernel",
                          "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": int(alg_bytes)},

@@ -366,8 +366,17 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
     p.out_cmps = d_cmps;
     p.out_hops = d_hops;
     SearchLaunch l;
-    rc = plan_search(p, l, g_sm_count, std::max(idx->n_slots, affordable_slots(idx)));
+    // cudaMemGetInfo (affordable_slots) costs milliseconds and serialises with the device: only ask when this launch wants
+    // more slots than already have tag arrays
+    rc = plan_search(p, l, g_sm_count, 0xffffffffu);
     if (rc != RG_OK) return rc;
+    if (l.grid * l.warps_per_cta > idx->n_slots) {
+        const uint32_t cap = std::max(idx->n_slots, affordable_slots(idx));
+        if (l.grid * l.warps_per_cta > cap) {
+            rc = plan_search(p, l, g_sm_count, cap);
+            if (rc != RG_OK) return rc;
+        }
+    }
     rc = ensure_tags(idx, l.grid * l.warps_per_cta);
     if (rc != RG_OK) return rc;
     p.tags = idx->d_tags;

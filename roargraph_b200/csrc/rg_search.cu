@@ -747,12 +747,30 @@ template <bool kL2, int kMode, int kMinBlocks, bool kVt = false>
 int launch_v(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
     auto kern = beam_search_kernel<kL2, kMode, kMinBlocks, kVt>;
     RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+    static const bool trace = getenv("RG_TRACE_SEARCH") != nullptr;  // diagnostic: device time of each phase, synchronises
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace) {
+        for (auto &e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], s);
+    }
     RG_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), s));
     RG_CUDA(cudaMemsetAsync(p.stats, 0, 4 * sizeof(unsigned long long), s));
+    if (trace) cudaEventRecord(ev[1], s);
     int rc = maintain_tags(p, l, s);
     if (rc != RG_OK) return rc;
+    if (trace) cudaEventRecord(ev[2], s);
     kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
     RG_CUDA(cudaGetLastError());
+    if (trace) {
+        cudaEventRecord(ev[3], s);
+        cudaStreamSynchronize(s);
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c, ev[2], ev[3]);
+        fprintf(stderr, "[rg search] memsets %.3f ms, tag maintenance %.3f ms, kernel %.3f ms\n", a, b, c);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     return RG_OK;
 }
 
