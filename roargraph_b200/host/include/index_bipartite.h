@@ -12,6 +12,9 @@
 //   SearchBipartiteGraph(...)                           :137 batch of one through SearchBipartiteGraphBatch
 //   LoadLearnBaseKNN                                    :109 reads the ids of the training queries' kNN file
 //   BuildRoarGraph(n_sq, sq, n_bp, bp, params)          :38  device build (rg_index_build_roargraph)
+//   BuildBipartite(n_sq, sq, n_bp, bp, params)          :36  host assembly of the raw bipartite graph from the kNN lists
+//                                                            (qbaseNNbipartite, src/index_bipartite.cpp:235-280: pure id
+//                                                            shuffling, no distances); uploaded on the first search
 //   SaveProjectionGraph                                 :103 same file format
 //   GetProjectionGraph                                  :113 host copy of the adjacency lists
 //   need_normalize                                      :145
@@ -56,6 +59,9 @@ class IndexBipartite : public Index {
   void InitVisitedListPool(uint32_t num_threads) { (void)num_threads; }
 
   void BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data, const Parameters &parameters);
+  // bp_data may be null when only the graph file is wanted (test_only_build_bipartite): the graph depends on the
+  // training queries' kNN lists alone
+  void BuildBipartite(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data, const Parameters &parameters);
 
   std::pair<uint32_t, uint32_t> SearchRoarGraph(const float *query, size_t k, size_t &qid, const Parameters &parameters,
                                                 unsigned *indices, std::vector<float> &res_dists);
@@ -84,11 +90,13 @@ class IndexBipartite : public Index {
  protected:
   void EnsureDeviceIndex();
   void UploadProjectionGraph();
+  void UploadBipartiteGraph();
   [[noreturn]] void Fail(int rc) const;
 
   CompactGraph bipartite_graph_;
   CompactGraph projection_graph_;
   bool projection_host_valid_ = false;
+  bool bipartite_uploaded_ = false;
   std::vector<std::vector<uint32_t>> learn_base_knn_;
   uint32_t projection_ep_ = 0;
   float *owned_base_ = nullptr;

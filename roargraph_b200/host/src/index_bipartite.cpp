@@ -3,6 +3,7 @@
 // LoadLearnBaseKNN :2622-2642, LoadVectorData :2664-2695, "not enough results" :2408-2412.
 #include "index_bipartite.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -180,12 +181,83 @@ void IndexBipartite::Load(const char *filename) {
   in.read((char *)&npts, 4);
   double deg = 0;
   read_adjacency(in, npts, bipartite_graph_, deg);
+  bipartite_uploaded_ = false;
+  if (data_bp_) UploadBipartiteGraph();
+}
+
+void IndexBipartite::UploadBipartiteGraph() {
   EnsureDeviceIndex();
+  if (bipartite_graph_.size() < nd_) throw std::runtime_error("bipartite graph has fewer nodes than the base");
   std::vector<uint64_t> row_off;
   std::vector<uint32_t> nbrs;
   to_csr(bipartite_graph_, row_off, nbrs);
-  int rc = rg_index_set_bipartite(dev_, npts, row_off.data(), nbrs.data());
+  int rc = rg_index_set_bipartite(dev_, bipartite_graph_.size(), row_off.data(), nbrs.data());
   if (rc != RG_OK) Fail(rc);
+  bipartite_uploaded_ = true;
+}
+
+// BuildBipartite (:42-141) = qbaseNNbipartite (:235-280) as far as the saved graph goes: training query sq becomes node
+// nd + sq; its edges are its first M_pjbp nearest base rows except every occurrence of the top-1 (:262-269), and the
+// top-1 base row gets the reverse edge to nd + sq (:270-273).  The reference appends the reverse edges from OpenMP threads
+// under per-node locks, so their order within a base row depends on thread timing; here it is ascending sq, which is what
+// the reference produces with -T 1.  (CalculateProjectionep, :92, has no effect on the bipartite graph or its file.)
+void IndexBipartite::BuildBipartite(size_t n_sq, const float *sq_data, size_t n_bp, const float *bp_data,
+                                    const Parameters &parameters) {
+  std::cout << "start build bipartite index" << std::endl;
+  (void)sq_data;
+  const uint32_t M_pjbp = parameters.Get<uint32_t>("M_pjbp");
+  if (learn_base_knn_.size() < n_sq) throw std::runtime_error("LoadLearnBaseKNN must be called before BuildBipartite");
+  if (n_bp + n_sq > 0xffffffffull) throw std::invalid_argument("more than 2^32 nodes");
+  if (need_normalize && bp_data) {
+    std::cout << "normalizing base data" << std::endl;
+    float *d = const_cast<float *>(bp_data);
+    for (size_t i = 0; i < n_bp; ++i) normalize(d + i * dimension_, dimension_);
+  }
+  nd_sq_ = n_sq;
+  if (bp_data) SetBaseData(bp_data, n_bp);
+  else nd_ = n_bp;
+  const uint32_t u32_nd = (uint32_t)n_bp;
+  bipartite_graph_.assign(n_bp + n_sq, {});
+  for (size_t sq = 0; sq < n_sq; ++sq) {
+    std::vector<uint32_t> &nn_base = learn_base_knn_[sq];
+    if (nn_base.size() > M_pjbp) {
+      nn_base.resize(M_pjbp);
+      nn_base.shrink_to_fit();
+    }
+    if (nn_base.empty()) continue;
+    const uint32_t cur_tgt = nn_base[0];
+    if (cur_tgt >= u32_nd) throw std::runtime_error("learn-base kNN id out of range");
+    std::vector<uint32_t> &row = bipartite_graph_[n_bp + sq];
+    for (uint32_t id : nn_base) {
+      if (id == cur_tgt) continue;
+      if (id >= u32_nd) throw std::runtime_error("learn-base kNN id out of range");
+      row.push_back(id);
+    }
+    bipartite_graph_[cur_tgt].push_back((uint32_t)sq + u32_nd);
+  }
+  std::cout << "100% of save bipartite graph finish" << std::endl;
+  double deg_b = 0, deg_q = 0;
+  size_t max_b = 0, min_b = (size_t)-1, max_q = 0, min_q = (size_t)-1;
+  for (size_t i = 0; i < bipartite_graph_.size(); ++i) {
+    const size_t d = bipartite_graph_[i].size();
+    if (i < n_bp) {
+      deg_b += d;
+      max_b = std::max(max_b, d);
+      min_b = std::min(min_b, d);
+    } else {
+      deg_q += d;
+      max_q = std::max(max_q, d);
+      min_q = std::min(min_q, d);
+    }
+  }
+  std::cout << "Bipartite nd degree avg: " << (n_bp ? deg_b / n_bp : 0) << std::endl;
+  std::cout << "Bipartite nd degree max: " << max_b << std::endl;
+  std::cout << "Bipartite nd degree min: " << (n_bp ? min_b : 0) << std::endl;
+  std::cout << "Bipartite nd_sq degree avg: " << (n_sq ? deg_q / n_sq : 0) << std::endl;
+  std::cout << "Bipartite nd_sq degree max: " << max_q << std::endl;
+  std::cout << "Bipartite nd_sq degree min: " << (n_sq ? min_q : 0) << std::endl;
+  bipartite_uploaded_ = false;
+  has_built = true;
 }
 
 void IndexBipartite::LoadLearnBaseKNN(const char *filename) {
@@ -263,6 +335,7 @@ void IndexBipartite::SearchBipartiteGraphBatch(const float *queries, size_t nq, 
                                                const uint32_t *init_ids, uint32_t n_init, uint64_t seed,
                                                unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
   const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");
+  if (!bipartite_uploaded_ && !bipartite_graph_.empty() && data_bp_) UploadBipartiteGraph();
   if (!dev_) throw std::runtime_error("index not loaded");
   int rc = rg_search_bipartite(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, init_ids, n_init, seed, indices, dists, cmps, hops);
   if (rc != RG_OK) Fail(rc);

@@ -144,3 +144,110 @@ def test_build_cli_then_search_cli(tmp_path, golden):
     assert p.returncode == 0, p.stdout + p.stderr
     t = _table(p.stdout)
     assert t[100][3] > 0.9  # recall@10 on the CLI-built index
+
+
+# ---- raw bipartite graph: test_only_build_bipartite -> test_search_bipartite ---------------------------------------------
+
+def _write_bipartite_inputs(tmp_path, golden):
+    bf, tf, kf = (str(tmp_path / n) for n in ("base.fbin", "train.fbin", "train.gt"))
+    F.write_fbin(bf, golden.base_raw)
+    knn = golden.z["train_knn_ids"]
+    # only the header of the training-query file is read on this path
+    F.write_fbin(tf, np.zeros((knn.shape[0], golden.base_raw.shape[1]), np.float32))
+    F.write_truthset(kf, knn, np.zeros(knn.shape, np.float32))
+    return bf, tf, kf
+
+
+def _build_bipartite_args(golden, bf, tf, kf, out, threads):
+    return ["--data_type", "float", "--dist", golden.metric, "--base_data_path", bf, "--sampled_query_data_path", tf,
+            "--bipartite_index_save_path", out, "--projection_index_save_path", out + ".unused", "--learn_base_nn_path", kf,
+            "--base_learn_nn_path", kf, "--M_pjbp", "16", "-T", str(threads)]
+
+
+def test_build_bipartite_cli_help_and_missing_arguments():
+    for exe, flag in (("test_only_build_bipartite", "--learn_base_nn_path"), ("test_search_bipartite", "--seed")):
+        p = run(exe, "--help")
+        assert p.returncode == 0 and flag in p.stdout
+        p = run(exe)
+        assert p.returncode == 255 and "required but missing" in p.stderr
+
+
+def test_build_bipartite_cli_needs_no_gpu_and_follows_qbaseNNbipartite(tmp_path, golden):
+    """The graph file is a pure function of the kNN ids: check it against the definition (gpu_helpers.bipartite_from_knn
+    restates src/index_bipartite.cpp:235-280)."""
+    from gpu_helpers import bipartite_from_knn
+    bf, tf, kf = _write_bipartite_inputs(tmp_path, golden)
+    out = str(tmp_path / "ours.bp")
+    p = run(*(["test_only_build_bipartite"] + _build_bipartite_args(golden, bf, tf, kf, out, 2)))
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Bipartite nd_sq degree max" in p.stdout and "Save index to" in p.stdout
+    row_off, nbrs = F.read_bipartite_index(out)
+    nd = golden.base_raw.shape[0]
+    want_off, want_nbrs = bipartite_from_knn(golden.z["train_knn_ids"], nd, 16)
+    assert (row_off == want_off).all() and (nbrs == want_nbrs).all()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_test_only_build_bipartite")), reason="oracle/_ref not available")
+def test_build_bipartite_cli_file_matches_reference_cli(tmp_path, golden):
+    """Single-threaded, the reference appends reverse edges in training-query order: the two files are byte-identical.
+    With more threads the order inside a base row depends on timing, the content does not."""
+    bf, tf, kf = _write_bipartite_inputs(tmp_path, golden)
+    ours, ref1, ref4 = (str(tmp_path / n) for n in ("ours.bp", "ref1.bp", "ref4.bp"))
+    p = run(*(["test_only_build_bipartite"] + _build_bipartite_args(golden, bf, tf, kf, ours, 1)))
+    assert p.returncode == 0, p.stdout + p.stderr
+    for out, threads in ((ref1, 1), (ref4, 4)):
+        r = subprocess.run([os.path.join(REF, "ref_test_only_build_bipartite")] + _build_bipartite_args(golden, bf, tf, kf, out, threads),
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    assert open(ours, "rb").read() == open(ref1, "rb").read()
+    o_off, o_n = F.read_bipartite_index(ours)
+    r_off, r_n = F.read_bipartite_index(ref4)
+    assert (o_off == r_off).all()
+    for i in np.flatnonzero(np.diff(o_off.astype(np.int64)) > 1):
+        a, b = int(o_off[i]), int(o_off[i + 1])
+        assert sorted(o_n[a:b]) == sorted(r_n[a:b])
+
+
+def _bipartite_table(stdout):
+    rows = {}
+    for ln in stdout.splitlines():
+        f = ln.split()
+        if len(f) == 7 and f[0].isdigit():
+            rows[int(f[0])] = [float(x) for x in f[1:]]  # qps, avg_cmps, mean_latency, recall, rderr, avg_hops
+    return rows
+
+
+@pytest.mark.gpu
+def test_build_bipartite_cli_then_search_bipartite_cli(tmp_path, golden):
+    bf, qf, gf, _ = _write_case(tmp_path, golden)
+    _, tf, kf = _write_bipartite_inputs(tmp_path, golden)
+    bp = str(tmp_path / "ours.bp")
+    p = run(*(["test_only_build_bipartite"] + _build_bipartite_args(golden, bf, tf, kf, bp, 2)))
+    assert p.returncode == 0, p.stdout + p.stderr
+    Ls = [10, 50, 200]
+    args = ["--data_type", "float", "--dist", golden.metric, "--base_data_path", bf, "--sampled_query_data_path", tf,
+            "--query_path", qf, "--gt_path", gf, "--bipartite_index_save_path", bp, "--projection_index_save_path",
+            bp + ".unused", "--L_pq", *map(str, Ls), "--k", "10", "-T", "2"]
+    csv = str(tmp_path / "eval.csv")
+    a = subprocess.run([os.path.join(BIN, "test_search_bipartite"), *args, "--evaluation_save_path", csv],
+                       capture_output=True, text=True)
+    assert a.returncode == 0, a.stdout + a.stderr
+    b = subprocess.run([os.path.join(BIN, "test_search_bipartite"), *args], capture_output=True, text=True)
+    ta, tb = _bipartite_table(a.stdout), _bipartite_table(b.stdout)
+    assert sorted(ta) == Ls
+    for L in Ls:  # seeded entry points: everything but the timing columns repeats exactly
+        assert ta[L][1] == tb[L][1] and ta[L][3:] == tb[L][3:]
+    assert ta[200][3] >= ta[10][3] and ta[200][3] > 0.8
+    lines = open(csv).read().strip().splitlines()
+    assert len(lines) == len(Ls) and all(len(l.split(",")) == 7 for l in lines)  # the reference's 7 columns
+    ref_exe = os.path.join(REF, "ref_test_search_bipartite")
+    if os.path.exists(ref_exe):
+        # the reference's entry points are unseeded random: compare the statistics, not the ids
+        r = subprocess.run([ref_exe, *args], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        tr = _bipartite_table(r.stdout)
+        assert sorted(tr) == Ls
+        for L in Ls:
+            assert ta[L][3] == pytest.approx(tr[L][3], abs=0.06), (L, ta[L], tr[L])        # recall
+            assert ta[L][1] == pytest.approx(tr[L][1], rel=0.15), (L, ta[L], tr[L])        # avg cmps
+            assert ta[L][5] == pytest.approx(tr[L][5], rel=0.15), (L, ta[L], tr[L])        # avg hops
