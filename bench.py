@@ -178,9 +178,12 @@ def time_knn(a, w, dev, world, K=100, reps=2):
                     + (", all-gather + k-way merge over the shards" if world > 1 else "")}
 
 
-def time_reference_cpu(a, w, L, want_sample_s=15.0):
-    """The unmodified reference SearchRoarGraph (oracle/_ref/libref_roargraph.so) on the host cores over this index:
-    100-query serial warm-up then omp parallel for schedule(dynamic,1), as tests/test_search_roargraph.cpp:198-209."""
+def time_reference_cpu(a, w, L, steps, warmup, budget_s):
+    """The unmodified reference SearchRoarGraph (oracle/_ref/libref_roargraph.so) on the host cores over this index, under
+    the reference CLI's loop shape (100-query serial warm-up, then omp parallel for schedule(dynamic,1),
+    tests/test_search_roargraph.cpp:198-209).  One step = one pass over a bounded sample of the query batch (the first
+    n_sample queries, sized so that warmup + steps passes take about budget_s); `warmup` untimed passes, then exactly
+    `steps` timed ones; value = n_sample * steps / their total wall time."""
     from oracle.oracle import Reference
     from roargraph_b200 import formats as F
     from roargraph_b200.workload import log, recall_at_k
@@ -198,22 +201,24 @@ def time_reference_cpu(a, w, L, want_sample_s=15.0):
     os.remove(ipath)
     log(f"reference index in host memory ({time.time() - t0:.1f}s), {cores} host threads")
     q = w.queries_host
-    # bounded sample: time a small slice first, then as many whole passes over the batch as fit the budget
+    # size the sample on a small slice (this call also does the CLI's 100-query serial warm-up)
     r0 = R.search_roargraph(h, q[:min(len(q), 1000)], a.k, L, cores, warmup=True)
     qps_est = min(len(q), 1000) / max(r0["wall_s"], 1e-6)
-    n_sample = int(min(len(q), max(1000, qps_est * want_sample_s)))
+    n_sample = int(min(len(q), max(1000, qps_est * budget_s / max(1, steps + warmup))))
+    for _ in range(warmup):
+        R.search_roargraph(h, q[:n_sample], a.k, L, cores, warmup=False)
     walls, res = [], None
-    reps = int(max(1, min(5, (qps_est * want_sample_s) // max(n_sample, 1))))
-    for _ in range(reps):
+    for _ in range(steps):
         res = R.search_roargraph(h, q[:n_sample], a.k, L, cores, warmup=False)
         walls.append(res["wall_s"])
     R.index_free(h)
-    best = min(walls)
+    total = float(sum(walls))
     rec = recall_at_k(res["ids"], w.gt_ids[:n_sample], a.k)
-    return {"value": n_sample / best, "unit": "queries/s", "cores": cores, "kind": "reference",
-            "sample": f"first {n_sample} of {len(q)} queries at L_pq={L}, best of {reps} passes after the CLI's "
-                      f"100-query warm-up; recall@{a.k}={rec:.4f}",
-            "ms_per_pass": best * 1e3, "n_sample": n_sample, "res": res}
+    return {"value": n_sample * steps / total, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"first {n_sample} of {len(q)} queries at L_pq={L} per step, {steps} timed passes after {warmup} "
+                      f"untimed ones and the CLI's 100-query serial warm-up; recall@{a.k}={rec:.4f}",
+            "ms_per_step": total / steps * 1e3, "step_ms": [round(x * 1e3, 3) for x in walls], "n_sample": n_sample,
+            "res": res}
 
 
 def main():
@@ -284,18 +289,17 @@ def main():
     L = L_star
 
     if a.impl == "reference":
-        cpu = time_reference_cpu(a, w, L, want_sample_s=20.0)
-        # K timed steps of the bounded sample were folded into time_reference_cpu's passes; report its best pass
+        cpu = time_reference_cpu(a, w, L, steps=a.steps, warmup=a.warmup, budget_s=90.0)
         line = {
             "impl": "reference", "metric": f"QPS@recall{k}>={a.target_recall}", "value": cpu["value"], "unit": "queries/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cpu["ms_per_pass"],
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cpu["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "L_pq": L, "recall": rec_star,
                        "note": "unmodified reference SearchRoarGraph on the host cores; inputs (base, index, ground "
                                "truth) were produced on the GPU before the timed region"},
             "cpu_baseline": {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cpu["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "step_ms": cpu["step_ms"],
         }
         print(json.dumps(line), flush=True)
         return 0
@@ -434,7 +438,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            cpu = time_reference_cpu(a, w, L, want_sample_s=15.0)
+            cpu = time_reference_cpu(a, w, L, steps=5, warmup=1, budget_s=20.0)
             n_s = cpu["n_sample"]
             same = bool((cpu["res"]["ids"] == e2e_ids[:n_s]).all())
             cpu_out = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}

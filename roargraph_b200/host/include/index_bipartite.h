@@ -22,6 +22,7 @@
 // where the reference's CLI runs `#pragma omp parallel for` over SearchRoarGraph (tests/test_search_roargraph.cpp:203).
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -100,7 +101,9 @@ class IndexBipartite : public Index {
   std::vector<std::vector<uint32_t>> learn_base_knn_;
   uint32_t projection_ep_ = 0;
   float *owned_base_ = nullptr;
+  size_t dev_dim_ = 0;  // row stride on the device when it differs from GetDimension() (unpadded build input)
   rg_index *dev_ = nullptr;
+  std::mutex call_mutex_;  // one caller at a time per rg_index
 };
 
 }  // namespace efanna2e

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <stdexcept>
 
 #include "rg_b200.h"
@@ -65,7 +66,7 @@ void IndexBipartite::Fail(int rc) const {
 void IndexBipartite::EnsureDeviceIndex() {
   if (dev_) return;
   if (!data_bp_) throw std::runtime_error("base data not loaded");
-  int rc = rg_index_create(&dev_, data_bp_, nd_, (uint32_t)dimension_, to_rg_metric(metric_), 0);
+  int rc = rg_index_create(&dev_, data_bp_, nd_, (uint32_t)(dev_dim_ ? dev_dim_ : dimension_), to_rg_metric(metric_), 0);
   if (rc != RG_OK) Fail(rc);
 }
 
@@ -214,8 +215,13 @@ void IndexBipartite::BuildBipartite(size_t n_sq, const float *sq_data, size_t n_
     for (size_t i = 0; i < n_bp; ++i) normalize(d + i * dimension_, dimension_);
   }
   nd_sq_ = n_sq;
-  if (bp_data) SetBaseData(bp_data, n_bp);
-  else nd_ = n_bp;
+  // the graph is assembled on the host; the base goes to HBM with the first search (a build-only run needs no GPU)
+  if (dev_) {
+    rg_index_destroy(dev_);
+    dev_ = nullptr;
+  }
+  data_bp_ = bp_data;
+  nd_ = n_bp;
   const uint32_t u32_nd = (uint32_t)n_bp;
   bipartite_graph_.assign(n_bp + n_sq, {});
   for (size_t sq = 0; sq < n_sq; ++sq) {
@@ -288,6 +294,18 @@ void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_
     for (size_t i = 0; i < n_bp; ++i) normalize(d + i * dimension_, dimension_);
   }
   nd_sq_ = n_sq;
+  if (dimension_ % 8 != 0) {
+    // the reference's build CLI hands over raw fbin rows (tests/test_build_roargraph.cpp:105-107, data_align commented
+    // out); the device layout wants rows padded to x8 floats with zeros, which changes no distance
+    const size_t pd = (dimension_ + 7) / 8 * 8;
+    float *padded = (float *)calloc(n_bp * pd, sizeof(float));
+    if (!padded) throw std::runtime_error("out of host memory padding the base rows");
+    for (size_t i = 0; i < n_bp; ++i) memcpy(padded + i * pd, bp_data + i * dimension_, dimension_ * sizeof(float));
+    free(owned_base_);
+    owned_base_ = padded;
+    dev_dim_ = pd;
+    bp_data = padded;
+  }
   SetBaseData(bp_data, n_bp);
   const size_t nsq = learn_base_knn_.size();
   size_t stride = 0;
@@ -316,6 +334,9 @@ void IndexBipartite::Build(size_t n, const float *data, const Parameters &parame
 void IndexBipartite::SearchRoarGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
                                           unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
   const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");
+  // an rg_index takes one caller at a time; the reference's CLIs call SearchRoarGraph from an OpenMP loop on one shared
+  // index (tests/test_search_roargraph.cpp:203), so concurrent callers queue here
+  std::lock_guard<std::mutex> guard(call_mutex_);
   if (!dev_) throw std::runtime_error("index not loaded");
   int rc = rg_search_roargraph(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, indices, dists, cmps, hops);
   if (rc != RG_OK) Fail(rc);
@@ -335,6 +356,7 @@ void IndexBipartite::SearchBipartiteGraphBatch(const float *queries, size_t nq, 
                                                const uint32_t *init_ids, uint32_t n_init, uint64_t seed,
                                                unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
   const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");
+  std::lock_guard<std::mutex> guard(call_mutex_);
   if (!bipartite_uploaded_ && !bipartite_graph_.empty() && data_bp_) UploadBipartiteGraph();
   if (!dev_) throw std::runtime_error("index not loaded");
   int rc = rg_search_bipartite(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, init_ids, n_init, seed, indices, dists, cmps, hops);

@@ -251,3 +251,87 @@ def test_build_bipartite_cli_then_search_bipartite_cli(tmp_path, golden):
             assert ta[L][3] == pytest.approx(tr[L][3], abs=0.06), (L, ta[L], tr[L])        # recall
             assert ta[L][1] == pytest.approx(tr[L][1], rel=0.15), (L, ta[L], tr[L])        # avg cmps
             assert ta[L][5] == pytest.approx(tr[L][5], rel=0.15), (L, ta[L], tr[L])        # avg hops
+
+
+# ---- drop-in proof: the reference's CLI mains, compiled UNMODIFIED against the mirror (oracle/_ref/dropin_*) ----------------
+
+def _dropin(name):
+    return os.path.join(REF, "dropin_" + name)
+
+
+needs_dropin = pytest.mark.skipif(not os.path.exists(_dropin("test_search_roargraph")),
+                                  reason="oracle/_ref/dropin_* not built (needs /root/reference at build time)")
+
+
+@needs_dropin
+def test_reference_build_bipartite_main_on_the_mirror_writes_the_reference_file(tmp_path, golden):
+    bf, tf, kf = _write_bipartite_inputs(tmp_path, golden)
+    a, b = str(tmp_path / "dropin.bp"), str(tmp_path / "ref.bp")
+    for exe, out in ((_dropin("test_only_build_bipartite"), a), (os.path.join(REF, "ref_test_only_build_bipartite"), b)):
+        p = subprocess.run([exe] + _build_bipartite_args(golden, bf, tf, kf, out, 1), capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout + p.stderr
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+@needs_dropin
+@pytest.mark.skipif(has_cuda(), reason="only meaningful on a machine without a GPU")
+def test_reference_search_main_on_the_mirror_fails_loudly_without_gpu(tmp_path):
+    from conftest import GoldenCase
+    g = GoldenCase("ip_d40")
+    bf, qf, gf, idx = _write_case(tmp_path, g)
+    p = subprocess.run([_dropin("test_search_roargraph"), "--data_type", "float", "--dist", "ip", "--base_data_path", bf,
+                        "--query_path", qf, "--gt_path", gf, "--projection_index_save_path", idx, "--L_pq", "10", "--k", "10"],
+                       capture_output=True, text=True)
+    assert p.returncode != 0 and "no CUDA device" in p.stderr  # uncaught std::runtime_error in the reference's main
+
+
+@pytest.mark.gpu
+@needs_dropin
+def test_reference_search_main_on_the_mirror_prints_the_reference_table(tmp_path, golden):
+    """tests/test_search_roargraph.cpp as it is (OpenMP loop over SearchRoarGraph, one query per call) on the B200 library."""
+    bf, qf, gf, idx = _write_case(tmp_path, golden)
+    Ls = [10, 30, 100]
+    args = ["--data_type", "float", "--dist", golden.metric, "--base_data_path", bf, "--query_path", qf, "--gt_path", gf,
+            "--projection_index_save_path", idx, "--L_pq", *map(str, Ls), "--k", "10", "-T", "4"]
+    ours = subprocess.run([_dropin("test_search_roargraph"), *args], capture_output=True, text=True)
+    assert ours.returncode == 0, ours.stderr + ours.stdout
+    ref = subprocess.run([os.path.join(REF, "ref_test_search_roargraph"), *args], capture_output=True, text=True)
+    assert ref.returncode == 0, ref.stderr
+    to, tr = _table(ours.stdout), _table(ref.stdout)
+    assert sorted(to) == sorted(tr) == Ls
+    tol = 1e-3 if golden.metric == "cosine" else 1e-6
+    for L in Ls:
+        assert to[L][1] == pytest.approx(tr[L][1], rel=tol), (L, to[L], tr[L])   # avg cmps
+        assert to[L][3] == pytest.approx(tr[L][3], abs=tol + 1e-6)                # recall
+        assert to[L][4] == pytest.approx(tr[L][4], rel=tol)                       # avg hops
+
+
+@pytest.mark.gpu
+@needs_dropin
+def test_reference_build_and_bipartite_mains_on_the_mirror(tmp_path, golden):
+    import roargraph_b200 as rg
+    bf, qf, gf, _ = _write_case(tmp_path, golden)
+    tf, kf, idx = str(tmp_path / "train.fbin"), str(tmp_path / "train.gt"), str(tmp_path / "built.rg")
+    train = golden.test_raw
+    F.write_fbin(tf, train)
+    kmetric = "l2" if golden.metric == "l2" else ("cosine" if golden.metric == "cosine" else "ip")
+    ids, d = rg.knn(golden.base_raw, train, 50, kmetric)
+    F.write_truthset(kf, ids.astype(np.uint32), d)
+    p = subprocess.run([_dropin("test_build_roargraph"), "--data_type", "float", "--dist", golden.metric, "--base_data_path",
+                        bf, "--sampled_query_data_path", tf, "--projection_index_save_path", idx, "--learn_base_nn_path",
+                        kf, "--M_sq", "50", "--M_pjbp", "16", "--L_pjpq", "64", "-T", "2"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    ep, row_off, nbrs = F.read_projection_index(idx)
+    assert len(row_off) == golden.base.shape[0] + 1 and np.diff(row_off.astype(np.int64)).max() <= 32
+    # bipartite: reference build main -> reference search main, both on the mirror
+    _, tf2, kf2 = _write_bipartite_inputs(tmp_path, golden)
+    bp = str(tmp_path / "dropin.bp")
+    p = subprocess.run([_dropin("test_only_build_bipartite")] + _build_bipartite_args(golden, bf, tf2, kf2, bp, 2),
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    p = subprocess.run([_dropin("test_search_bipartite"), "--data_type", "float", "--dist", golden.metric, "--base_data_path",
+                        bf, "--sampled_query_data_path", tf2, "--query_path", qf, "--gt_path", gf,
+                        "--bipartite_index_save_path", bp, "--projection_index_save_path", bp + ".unused", "--L_pq", "200",
+                        "--k", "10", "-T", "4"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert _bipartite_table(p.stdout)[200][3] > 0.8

@@ -1,0 +1,40 @@
+"""Host-side mirror types (roargraph_b200/host/include/efanna2e) against the reference's own headers: compiled side by
+side from the same driver, traces must be identical.  Needs /root/reference (this container); skipped on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+REF_INC = "/root/reference/include"
+MIRROR_INC = os.path.join(ROOT, "roargraph_b200", "host", "include")
+DRIVER = os.path.join(ROOT, "tests", "cpp", "npq_driver.cpp")
+
+
+def _build(tmp_path, name, inc):
+    exe = str(tmp_path / name)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-w", "-I", inc, DRIVER, "-o", exe])
+    return exe
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_INC, "efanna2e", "neighbor.h")), reason="/root/reference not mounted")
+def test_neighbor_priority_queue_mirror_traces_equal_reference(tmp_path):
+    ref = _build(tmp_path, "npq_ref", REF_INC)
+    ours = _build(tmp_path, "npq_ours", MIRROR_INC)
+    for cap, n_ops, id_range, seed in ((1, 300, 8, 1), (4, 2000, 16, 2), (16, 5000, 64, 3), (100, 20000, 4000, 4),
+                                       (7, 3000, 7, 5)):
+        args = [str(cap), str(n_ops), str(id_range), str(seed)]
+        a = subprocess.run([ref, *args], capture_output=True, text=True, check=True).stdout
+        b = subprocess.run([ours, *args], capture_output=True, text=True, check=True).stdout
+        assert a == b and a.count("\n") > 3, (cap, n_ops, id_range, seed)
+
+
+def test_mirror_headers_are_self_contained(tmp_path):
+    """Every public header of the mirror compiles on its own (what a maintainer's include-path switch relies on)."""
+    for h in ("efanna2e/distance.h", "efanna2e/neighbor.h", "efanna2e/parameters.h", "efanna2e/util.h", "efanna2e/index.h",
+              "efanna2e/exceptions.h", "index_bipartite.h"):
+        src = tmp_path / "t.cpp"
+        src.write_text(f'#include "{h}"\nint main() {{ return 0; }}\n')
+        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", MIRROR_INC,
+                               "-I", os.path.join(ROOT, "include"), str(src)])
