@@ -11,7 +11,8 @@ canonical sweep (README.md:118) whose recall@10 against exact ground truth is >=
   roofline  algorithmic gather bytes of the search kernel / its CUDA-event duration vs the measured HBM copy peak
   cpu_baseline  the reference's own SearchRoarGraph (compiled unmodified, oracle/_ref) on the host cores, same index
 --impl reference prints the reference-CPU arm as the headline line instead (rank 0 only under torchrun).
-N > 1: base rows sharded over the ranks, per-shard index, one NCCL all-gather + merge kernel per step (strong scaling).
+N > 1: base rows sharded over the ranks, per-shard index, one NCCL all-gather + merge kernel per step (strong scaling);
+--shard query runs the comparison point instead: the full index on every rank, --nq queries per rank, one all-gather.
 """
 from __future__ import annotations
 
@@ -50,6 +51,9 @@ def parse_args():
     ap.add_argument("--cache_dir", default=os.environ.get("RG_BENCH_CACHE", "/tmp/rg_bench_cache"))
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_knn", action="store_true", help="skip the brute-force kNN leg")
+    ap.add_argument("--shard", default="base", choices=["base", "query"],
+                    help="N > 1: 'base' = base rows sharded, per-shard index, all-gather + merge (the contract, strong "
+                         "scaling); 'query' = full index replicated, --nq queries PER RANK, all-gather only (weak scaling)")
     ap.add_argument("--sweep", default="", help="also write the full L_pq sweep table (CSV) to this path")
     return ap.parse_args()
 
@@ -236,7 +240,7 @@ def main():
 
     import roargraph_b200 as rg
     from roargraph_b200 import workload as W
-    from roargraph_b200.sharded import ShardedRoarIndex
+    from roargraph_b200.sharded import ReplicatedRoarIndex, ShardedRoarIndex
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
@@ -249,11 +253,21 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         n_shards = world
 
-    w = W.build_search_workload(a.nb, a.dim, a.dist, a.ntrain, a.nq, a.k, a.M_sq, a.M_pjbp, a.L_pjpq, a.seed, local_rank,
+    replicas = world > 1 and a.impl == "b200" and a.shard == "query"
+    if replicas:  # full index on every rank (same seed -> same data, deterministic build -> same graph), queries split
+        n_shards = 1
+    nq = a.nq * (world if replicas else 1)
+    w = W.build_search_workload(a.nb, a.dim, a.dist, a.ntrain, nq, a.k, a.M_sq, a.M_pjbp, a.L_pjpq, a.seed, local_rank,
                                 shard=rank if n_shards > 1 else 0, n_shards=n_shards, cache_dir=a.cache_dir)
-    sidx = ShardedRoarIndex(w.index, w.row_lo)
-    nq, k = a.nq, a.k
+    k = a.k
     d_q = w.d_queries
+    if replicas:
+        ridx = ReplicatedRoarIndex(w.index)
+        d_q_local = d_q[rank * a.nq:(rank + 1) * a.nq]  # this rank's rows (a view); also the kernel-only / roofline pass
+    else:
+        sidx = ShardedRoarIndex(w.index, w.row_lo)
+        d_q_local = d_q
+    nq_local = d_q_local.shape[0]
     d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
     d_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
     d_cmps = torch.empty(nq, dtype=torch.int32, device=dev)
@@ -261,8 +275,9 @@ def main():
     stream = torch.cuda.current_stream()
 
     def run_dev(L):
-        n = sidx.search_dev(d_q, k, L, d_ids, d_dists, d_cmps, d_hops)
-        return n
+        if replicas:
+            return ridx.search_dev(d_q, k, L, d_ids, d_dists) + 1  # + the all-gather
+        return sidx.search_dev(d_q, k, L, d_ids, d_dists, d_cmps, d_hops)
 
     # ---- calibrate L_pq on recall (outside the timed region) ------------------------------------------------------
     sweep_rows = []
@@ -334,18 +349,15 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / a.steps
     qps = nq / (ms_per_step / 1e3)
-    st = w.index.last_stats()
-    ll = w.index.last_launch()
-
     # kernel-only duration for the roofline (search kernel alone on this rank, same stream, L2 flushed)
     kern_ms = []
-    loc_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    loc_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    loc_i = torch.empty((nq_local, k), dtype=torch.int32, device=dev)
+    loc_d = torch.empty((nq_local, k), dtype=torch.float32, device=dev)
     for s in range(min(a.steps, 10)):
         flush.fill_(s & 0xff)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        w.index.search_dev(d_q, k, L, loc_i, loc_d, d_cmps, d_hops, stream=stream)
+        w.index.search_dev(d_q_local, k, L, loc_i, loc_d, d_cmps[:nq_local], d_hops[:nq_local], stream=stream)
         e1.record(stream)
         torch.cuda.synchronize(dev)
         kern_ms.append(e0.elapsed_time(e1))
@@ -353,7 +365,9 @@ def main():
                                                 "note": getattr(sampler, "err", "NVML unavailable")}
     # median: every 255th query of a slot clears its visited-tag array (VisitedList::reset), which lands in one launch
     kern_avg_ms = float(np.median(kern_ms))
-    alg_bytes = (st["cmps"] + nq) * w.d_base.shape[1] * 4 + st["adj_words"] * 4
+    st = w.index.last_stats()   # of the kernel-only pass: this rank's queries on this rank's index
+    ll = w.index.last_launch()
+    alg_bytes = (st["cmps"] + nq_local) * w.d_base.shape[1] * 4 + st["adj_words"] * 4
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (kern_avg_ms / 1e3) / 1e9
 
@@ -389,14 +403,22 @@ def main():
             torch.cuda.synchronize(dev)
             dist.barrier()
             t0 = time.perf_counter()
-            e2e_ids, _ = sidx.search(hq.numpy(), k, L)
+            if replicas:  # this rank's slice H2D, search, all-gather, the whole result D2H
+                d_q_local.copy_(hq[rank * a.nq:(rank + 1) * a.nq], non_blocking=True)
+                ridx.search_dev(d_q, k, L, d_ids, d_dists)
+                h_ids.copy_(d_ids, non_blocking=True)
+                h_d.copy_(d_dists, non_blocking=True)
+                w.index.check(stream)
+                e2e_ids = h_ids.numpy().view(np.uint32)
+            else:
+                e2e_ids, _ = sidx.search(hq.numpy(), k, L)
             t1 = time.perf_counter()
             if s >= a.warmup:
                 e2e_ms.append((t1 - t0) * 1e3)
         t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = [float(t.item())]
-        h2d = hq.numel() * 4
+        h2d = hq.numel() * 4 // (world if replicas else 1)
         d2h = nq * k * 8
     e2e_qps = nq / (float(np.mean(e2e_ms)) / 1e3)
     e2e_recall = W.recall_at_k(e2e_ids, w.gt_ids, k)
@@ -429,7 +451,7 @@ def main():
         sweep_table = a.sweep
 
     knn_out = None
-    if not a.no_knn:
+    if not a.no_knn and not replicas:  # the kNN leg shards the BASE (configs[3]); replicas hold all of it
         try:
             knn_out = time_knn(a, w, dev, world)
         except Exception as e:  # noqa: BLE001
@@ -452,11 +474,14 @@ def main():
         line = {
             "metric": f"QPS@recall{k}>={a.target_recall}", "value": qps, "unit": "queries/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if replicas else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "L_pq": L, "recall": rec_star, "e2e_recall": e2e_recall,
-                       "sharding": f"base rows over {world} rank(s), per-shard index, all-gather + merge" if world > 1 else "none",
+                       "sharding": (f"queries over {world} replicas of the full index ({a.nq} queries per rank), all-gather"
+                                    if replicas else
+                                    f"base rows over {world} rank(s), per-shard index, all-gather + merge" if world > 1
+                                    else "none"),
                        "l2": "256 MiB fill between steps (outside the timed events); touched rows >> 126 MB L2",
-                       "avg_cmps": st["cmps"] / nq, "avg_hops": st["hops"] / nq, "launch": ll, "setup": w.info},
+                       "avg_cmps": st["cmps"] / nq_local, "avg_hops": st["hops"] / nq_local, "launch": ll, "setup": w.info},
             "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": float(np.mean(e2e_ms)), "step_ms": [round(float(x), 3) for x in e2e_ms]},

@@ -112,6 +112,68 @@ class ShardedRoarIndex:
         return b["h_i"].numpy().view(np.uint32), b["h_d"].numpy()
 
 
+class ReplicatedRoarIndex:
+    """Query-sharded mode ("replicas"): every rank holds the FULL base and the same RoarGraph, owns a
+    slice of the query batch, and the per-rank result blocks are collected with one all-gather — no merge step, and the
+    ids are those of the single-GPU search.  The comparison point for the base-sharded contract: G x the memory, the
+    same work per query, throughput ~ linear in G; base-sharding does G x the work per query at a smaller L_pq.
+
+    Every rank must own the same number of queries (all_gather_into_tensor), so the batch is padded by repeating the
+    last query of a short slice; search_dev returns only the real rows."""
+
+    def __init__(self, index, group=None, local_search=None):
+        import torch.distributed as dist
+
+        self.index = index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._local = local_search  # tests inject a checker; default = the CUDA search on torch's current stream
+        self._buf = {}
+
+    def _search_local(self, d_q, k, L_pq, out_ids, out_dists):
+        if self._local is not None:
+            return self._local(d_q, k, L_pq, out_ids, out_dists)
+        import torch
+        self.index.search_dev(d_q, k, L_pq, out_ids, out_dists, None, None, stream=torch.cuda.current_stream())
+
+    def search_dev(self, d_q_all, k: int, L_pq: int, out_ids, out_dists) -> int:
+        """d_q_all: the WHOLE batch [nq, dim] on this rank's device (only this rank's slice is read);
+        out_ids / out_dists: [nq, k], complete on every rank afterwards.  Returns the number of kernels launched."""
+        import torch
+        import torch.distributed as dist
+
+        nq = d_q_all.shape[0]
+        if self.world == 1:
+            self._search_local(d_q_all, k, L_pq, out_ids, out_dists)
+            return 1
+        per = -(-nq // self.world)
+        lo = min(self.rank * per, nq)
+        hi = min(lo + per, nq)
+        key = (per, k, d_q_all.device)
+        if key not in self._buf:
+            self._buf[key] = (torch.empty((per, d_q_all.shape[1]), dtype=d_q_all.dtype, device=d_q_all.device),
+                              torch.zeros((per, k), dtype=out_ids.dtype, device=d_q_all.device),
+                              torch.zeros((per, k), dtype=out_dists.dtype, device=d_q_all.device),
+                              torch.empty((self.world * per, k), dtype=out_ids.dtype, device=d_q_all.device),
+                              torch.empty((self.world * per, k), dtype=out_dists.dtype, device=d_q_all.device))
+        q_loc, loc_i, loc_d, all_i, all_d = self._buf[key]
+        launches = 0
+        if hi - lo == per:
+            self._search_local(d_q_all[lo:hi], k, L_pq, loc_i, loc_d)  # rows of a row-major batch: contiguous, in place
+            launches = 1
+        elif hi > lo:
+            q_loc[:hi - lo].copy_(d_q_all[lo:hi])
+            q_loc[hi - lo:].copy_(d_q_all[hi - 1:hi].expand(per - (hi - lo), -1))
+            self._search_local(q_loc, k, L_pq, loc_i, loc_d)
+            launches = 1
+        dist.all_gather_into_tensor(all_i, loc_i, group=self.group)
+        dist.all_gather_into_tensor(all_d, loc_d, group=self.group)
+        out_ids.copy_(all_i[:nq])   # rank r's block starts at r * per: contiguous in query order, padding only at the end
+        out_dists.copy_(all_d[:nq])
+        return launches
+
+
 def sharded_knn_dev(d_base_shard, d_queries, K: int, metric, row_lo: int, group=None, batch: int = 1 << 20,
                     local_knn=None, merge=None):
     """Brute-force kNN with the BASE sharded over the ranks of `group` (BASELINE.json configs[3]): every rank scores all

@@ -109,3 +109,45 @@ def test_two_rank_sharded_knn(tmp_path, oracle):
     full_i, full_d = oracle.exact_knn(g.base_raw, g.test_raw, 7, "l2")
     np.testing.assert_allclose(z["d"], full_d, rtol=1e-5, atol=1e-5)
     assert (z["i"] == full_i).mean() > 0.999
+
+
+def _replica_worker(rank, world, port, out, nq):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    from roargraph_b200.sharded import ReplicatedRoarIndex
+    O = Oracle()
+    g = GoldenCase("ip_d40")
+    k, L = 10, 32
+    calls = []
+
+    def local_search(d_q, k_, L_, out_ids, out_dists):  # checker standing in for the CUDA search on this rank's slice
+        r = O.search_roargraph(g.base, g.row_off, g.nbrs, g.ep, g.metric, d_q.numpy(), k_, L_)
+        out_ids.copy_(torch.from_numpy(r["ids"].astype(np.int32)))
+        out_dists.copy_(torch.from_numpy(r["dists"]))
+        calls.append(d_q.shape[0])
+
+    ridx = ReplicatedRoarIndex(None, local_search=local_search)
+    q = torch.from_numpy(g.queries[:nq])
+    ids = torch.empty((nq, k), dtype=torch.int32)
+    dists = torch.empty((nq, k), dtype=torch.float32)
+    ridx.search_dev(q, k, L, ids, dists)
+    per = -(-nq // world)
+    assert calls == ([per] if rank * per < nq else [])  # every rank searches only its (padded) slice
+    if rank == 1:  # every rank holds the complete answer
+        np.savez(out, i=ids.numpy(), d=dists.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [64, 33, 1])
+def test_two_rank_query_sharded_replicas(tmp_path, oracle, nq):
+    """Replica mode: queries split over two ranks (ragged: 33 -> 17 + 16, 1 -> 1 + 0), one all-gather, no merge;
+    the result equals the single-process search id for id."""
+    out = str(tmp_path / "replica.npz")
+    mp.spawn(_replica_worker, args=(2, _free_port(), out, nq), nprocs=2, join=True)
+    z = np.load(out)
+    g = GoldenCase("ip_d40")
+    want = oracle.search_roargraph(g.base, g.row_off, g.nbrs, g.ep, g.metric, g.queries[:nq], 10, 32)
+    assert (z["i"].view(np.uint32) == want["ids"]).all()
+    assert (z["d"].view(np.uint32) == want["dists"].view(np.uint32)).all()
