@@ -50,6 +50,7 @@ struct SearchParams {
     uint32_t row_stride_smem; // floats; == dim padded so that (stride % 32) == 16 (bank-conflict-free float4 reads)
     uint32_t warp_smem_bytes; // bytes of dynamic smem per warp
     int metric_l2;            // 1: squared L2, 0: negative inner product
+    uint32_t merge_insert;    // 1: the candidates of a row group enter the queue in one merge pass (RG_QUEUE_MERGE, default 1)
     // L2-resident exact visited set (SearchRoarGraph only; see rg_search.cu "visited table"): per slot 2^vt_bbits buckets
     // of 16 x 16-bit entries; 0 = use the tag arrays
     uint32_t *vtab;           // n_slots x vt_words

@@ -220,6 +220,112 @@ __device__ __forceinline__ bool queue_insert(WarpCtx &w, uint32_t L, float cd, u
     return true;
 }
 
+// Up to 8 candidates of one row group (held by the lanes with (lane & 3) == 0, `pass` set) merged into the queue in ONE pass
+// over the tail instead of one shift per candidate.  Sequential NeighborPriorityQueue::insert calls leave the queue as "the L
+// smallest (distance, id) of everything seen, first unexpanded entry under the cursor" whatever their order,
+// so the merge is observably identical: every candidate finds its upper bound among the current entries by its own binary
+// search (all in parallel), exact duplicates are dropped as at neighbor.h:161, the accepted candidates are ranked among
+// themselves, entry j moves up by the number of candidates that land at or before it, and whatever ends beyond L falls
+// off.  Long queues pay O(L / 32) once per group instead of once per candidate.
+// `unique_ids`: the group's ids are pairwise distinct (true for every visited-filtered adjacency list; false for the bipartite
+// search's random entry points, which may repeat and then go through the one-by-one insert whose duplicate check drops them).
+template <bool kPrefetch>
+__device__ __forceinline__ void queue_insert_group(WarpCtx &w, const SearchParams &p, float d, uint32_t id, bool pass,
+                                                   bool unique_ids) {
+    const int lane = w.lane;
+    const uint32_t L = p.L;
+    uint32_t m = __ballot_sync(kFull, pass);
+    if (!m) return;
+    if (!p.merge_insert || !unique_ids || (m & (m - 1)) == 0) {  // one candidate, possible repeats, or merge off: plain insert
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(kFull, d, src);
+            const uint32_t cid = __shfl_sync(kFull, id, src);
+            const bool in = queue_insert(w, L, cd, cid);
+            if (kPrefetch && in) {
+                // the candidate sits in the top-L now and will very likely be expanded (hops ~= L):
+                // pull its adjacency row towards L2 so the dependent read at expansion time is short.
+                const char *a = reinterpret_cast<const char *>(p.adj + (size_t)cid * p.adj_stride);
+                const uint32_t bytes = p.adj_stride * 4u;
+                if ((uint32_t)lane * 32u < bytes) prefetch_l2(a + lane * 32u);
+            }
+        }
+        return;
+    }
+    float *qd = w.qd;
+    uint32_t *qi = w.qi;
+    const uint32_t size = w.size;
+    // upper bound of this lane's candidate among the entries (binary search per candidate lane, in parallel)
+    uint32_t pos = 0xffffffffu;
+    if (pass) {
+        uint32_t lo = 0, hi = size;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (nbr_less(d, id, qd[mid], qi[mid] & kIdMask)) hi = mid;
+            else lo = mid + 1;
+        }
+        const bool dup = lo > 0 && (qi[lo - 1] & kIdMask) == id && qd[lo - 1] == d;
+        if (!dup) pos = lo;
+    }
+    const uint32_t acc = __ballot_sync(kFull, pos != 0xffffffffu);
+    if (!acc) return;
+    // positions of the (up to 8) accepted candidates in every lane; rank of this lane's candidate among them
+    uint32_t posv[8];
+    uint32_t rank = 0, minpos = 0xffffffffu;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        posv[c] = __shfl_sync(kFull, pos, 4 * c);
+        const float od = __shfl_sync(kFull, d, 4 * c);
+        const uint32_t oi = __shfl_sync(kFull, id, 4 * c);
+        if (posv[c] != 0xffffffffu && nbr_less(od, oi, d, id)) ++rank;  // ids within a group are distinct
+        minpos = min(minpos, posv[c]);
+    }
+    const uint32_t fin = pos + rank;  // meaningful where pos is
+    const uint32_t newsize = min(size + (uint32_t)__popc(acc), L);
+    // entries [minpos, size) move up by the number of candidates landing at or before them, top chunk first: a chunk's
+    // targets lie at or above its own slots, all of which have been read (earlier chunks) or are being read (this one)
+    for (int top = (int)size - 1; top >= (int)minpos; top -= 32) {
+        const int j = top - lane;
+        const bool act = j >= (int)minpos;
+        float td = 0.f;
+        uint32_t ti = 0, nj = 0;
+        if (act) {
+            td = qd[j];
+            ti = qi[j];
+            uint32_t sh = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sh += (posv[c] <= (uint32_t)j) ? 1u : 0u;
+            nj = (uint32_t)j + sh;
+        }
+        __syncwarp();
+        if (act && nj < L) {
+            qd[nj] = td;
+            qi[nj] = ti;
+        }
+        __syncwarp();
+    }
+    const bool placed = pos != 0xffffffffu && fin < L;
+    if (placed) {
+        qd[fin] = d;
+        qi[fin] = id;  // flag = false (:174)
+    }
+    __syncwarp();
+    w.size = newsize;
+    if (minpos < w.cur) w.cur = minpos;  // the smallest accepted candidate has rank 0: it lands at minpos (< L, it beat the worst)
+    if (kPrefetch) {
+        uint32_t pm = __ballot_sync(kFull, placed);
+        while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const uint32_t cid = __shfl_sync(kFull, id, src);
+            const char *a = reinterpret_cast<const char *>(p.adj + (size_t)cid * p.adj_stride);
+            const uint32_t bytes = p.adj_stride * 4u;
+            if ((uint32_t)lane * 32u < bytes) prefetch_l2(a + lane * 32u);
+        }
+    }
+}
+
 // NeighborPriorityQueue::closest_unexpanded (neighbor.h:185-192): flag entry `cur`, advance to the next unflagged one.
 __device__ __forceinline__ uint32_t queue_pop(WarpCtx &w, float *dist_out = nullptr) {
     const uint32_t u = w.qi[w.cur] & kIdMask;
@@ -244,7 +350,8 @@ __device__ __forceinline__ uint32_t queue_pop(WarpCtx &w, float *dist_out = null
 
 // Evaluate cand[0..n) against the query and insert them: gather rows with bulk copies, 8 rows per mbarrier group.
 template <bool kL2>
-__device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj) {
+__device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj,
+                                                    bool unique_ids) {
     const int lane = w.lane;
     const uint32_t R = p.rows_per_batch;
     const uint32_t row_bytes = p.dim * 4u;
@@ -270,21 +377,8 @@ __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchPara
             const uint32_t id = valid ? w.cand[b0 + r] : 0u;
             bool pass = valid && t == 0;
             if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
-            uint32_t m = __ballot_sync(kFull, pass);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float cd = __shfl_sync(kFull, d, src);
-                const uint32_t cid = __shfl_sync(kFull, id, src);
-                const bool in = queue_insert(w, p.L, cd, cid);
-                if (in && prefetch_adj) {
-                    // the candidate sits in the top-L now and will very likely be expanded (hops ~= L):
-                    // pull its adjacency row towards L2 so the dependent read at expansion time is short.
-                    const char *a = reinterpret_cast<const char *>(p.adj + (size_t)cid * p.adj_stride);
-                    const uint32_t bytes = p.adj_stride * 4u;
-                    if ((uint32_t)lane * 32u < bytes) prefetch_l2(a + lane * 32u);
-                }
-            }
+            if (prefetch_adj) queue_insert_group<true>(w, p, d, id, pass, unique_ids);
+            else queue_insert_group<false>(w, p, d, id, pass, unique_ids);
         }
         __syncwarp();
     }
@@ -294,7 +388,8 @@ __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchPara
 // as soon as group g has been read, so eight rows stay in flight while the warp computes distances and inserts — the
 // single-buffered loop above has nothing in flight during that time.  Insertion order is unchanged (groups in order).
 template <bool kL2>
-__device__ __forceinline__ void evaluate_candidates_db(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj) {
+__device__ __forceinline__ void evaluate_candidates_db(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj,
+                                                       bool unique_ids) {
     const int lane = w.lane;
     const uint32_t row_bytes = p.dim * 4u;
     const uint32_t rstride = p.row_stride_smem;
@@ -327,27 +422,17 @@ __device__ __forceinline__ void evaluate_candidates_db(WarpCtx &w, const SearchP
         if (g + 2 < ngroups) issue(g + 2);
         bool pass = valid && t == 0;
         if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
-        uint32_t m = __ballot_sync(kFull, pass);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float cd = __shfl_sync(kFull, d, src);
-            const uint32_t cid = __shfl_sync(kFull, id, src);
-            const bool in = queue_insert(w, p.L, cd, cid);
-            if (in && prefetch_adj) {
-                const char *a = reinterpret_cast<const char *>(p.adj + (size_t)cid * p.adj_stride);
-                const uint32_t bytes = p.adj_stride * 4u;
-                if ((uint32_t)lane * 32u < bytes) prefetch_l2(a + lane * 32u);
-            }
-        }
+        if (prefetch_adj) queue_insert_group<true>(w, p, d, id, pass, unique_ids);
+        else queue_insert_group<false>(w, p, d, id, pass, unique_ids);
     }
     __syncwarp();
 }
 
 template <bool kL2>
-__device__ __forceinline__ void evaluate(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj) {
-    if (p.rows_per_batch == 16u) evaluate_candidates_db<kL2>(w, p, n, prefetch_adj);
-    else evaluate_candidates<kL2>(w, p, n, prefetch_adj);
+__device__ __forceinline__ void evaluate(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj,
+                                         bool unique_ids = true) {
+    if (p.rows_per_batch == 16u) evaluate_candidates_db<kL2>(w, p, n, prefetch_adj, unique_ids);
+    else evaluate_candidates<kL2>(w, p, n, prefetch_adj, unique_ids);
 }
 
 // Visited filter (visited_list_pool.h / src/index_bipartite.cpp:2378-2386): appends the not-yet-visited ids of
@@ -593,7 +678,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 __stcg(tags + id, (uint8_t)epoch);  // :306 entry points are marked visited
             }
             __syncwarp();
-            evaluate<kL2>(w, p, p.n_init, false);
+            evaluate<kL2>(w, p, p.n_init, false, /*unique_ids=*/false);  // random entry points may repeat
         }
 
         while (w.cur < w.size) {  // has_unexpanded_node
@@ -786,27 +871,13 @@ int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
 
 uint32_t max_search_slots(int sm_count) { return (uint32_t)sm_count * 32u; }
 
-int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slots) {
-    const uint32_t dim = p.dim;
-    p.row_stride_smem = dim + ((16u + 32u - (dim & 31u)) & 31u);  // stride % 32 == 16 -> conflict-free float4 reads
-    uint32_t R = env_u32("RG_ROWS_PER_BATCH", 8);
-    if (R < 8) R = 8;
-    if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
-    R &= ~7u;
-    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
-    while (wb > kMaxSmemPerCta && R > 8) {
-        R -= 8;
-        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
-    }
-    if (wb > kMaxSmemPerCta) {
-        set_error("L_pq / dim too large for one warp's shared-memory working set");
-        return RG_EINVAL;
-    }
-    // Warps per CTA: 4 unless a finer CTA granularity keeps more warps resident (long queues: the per-warp working set
-    // grows with L_pq, and whole 4-warp CTAs then waste up to a third of the shared memory).  At most 32 warps per SM
-    // (64 registers per thread), at most 32 CTAs per SM.
-    uint32_t warps = 4, ctas = 0;
-    const uint32_t env_warps = env_u32("RG_WARPS_PER_CTA", 0);
+// Warps per CTA and CTAs per SM for a per-warp working set of `wb` bytes: 4 warps per CTA unless a finer CTA granularity
+// keeps more warps resident (long queues: the per-warp working set grows with L_pq, and whole 4-warp CTAs then waste up to
+// a third of the shared memory).  At most 32 warps per SM (64 registers per thread), at most 32 CTAs per SM.
+// Returns the resident warps per SM (0: one warp does not fit).
+static uint32_t resident_geometry(uint32_t wb, uint32_t env_warps, uint32_t &warps, uint32_t &ctas) {
+    warps = 4;
+    ctas = 0;
     uint32_t best_total = 0;
     for (uint32_t wc = 4; wc >= 1; wc >>= 1) {
         if (env_warps && wc != env_warps) continue;
@@ -820,6 +891,38 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
             ctas = c;
         }
     }
+    return best_total;
+}
+
+int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slots) {
+    const uint32_t dim = p.dim;
+    p.row_stride_smem = dim + ((16u + 32u - (dim & 31u)) & 31u);  // stride % 32 == 16 -> conflict-free float4 reads
+    const uint32_t env_warps = env_u32("RG_WARPS_PER_CTA", 0);
+    uint32_t warps = 4, ctas = 0;
+    uint32_t R = env_u32("RG_ROWS_PER_BATCH", 0);
+    if (R == 0) {
+        // Row ring: 8 rows single-buffered, or 2 x 8 double-buffered (eight rows stay in flight while the warp computes
+        // distances and inserts).  The second ring costs resident warps; measured on the 10 M x 200 L_pq sweep
+        // (profiles/r1_sweep_10M_ring.csv) it pays when the single-buffered geometry already saturates the memory system
+        // (>= 20 warps per SM) or when it keeps at least 72 % of the resident warps.
+        uint32_t w8c, c8, w16c, c16;
+        const uint32_t w8 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 8, p.L), env_warps, w8c, c8);
+        const uint32_t w16 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 16, p.L), env_warps, w16c, c16);
+        R = (w16 > 0 && (w8 >= 20 || w16 * 100u >= w8 * 72u)) ? 16u : 8u;
+    }
+    if (R < 8) R = 8;
+    if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
+    R &= ~7u;
+    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
+    while (wb > kMaxSmemPerCta && R > 8) {
+        R -= 8;
+        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
+    }
+    if (wb > kMaxSmemPerCta) {
+        set_error("L_pq / dim too large for one warp's shared-memory working set");
+        return RG_EINVAL;
+    }
+    resident_geometry(wb, env_warps, warps, ctas);
     if (ctas < 1) {
         warps = 1;
         ctas = 1;
@@ -832,6 +935,7 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     if (grid * warps > max_slots) grid = max_slots / warps;
     if (grid < 1) grid = 1;
     p.rows_per_batch = R;
+    p.merge_insert = env_u32("RG_QUEUE_MERGE", 1) ? 1u : 0u;
     p.warp_smem_bytes = wb;
     l.grid = grid;
     l.block = warps * 32;

@@ -177,6 +177,39 @@ def test_bipartite_parity(oracle, golden):
     idx.close()
 
 
+def test_bipartite_not_enough_results(oracle, golden):
+    """Ten entry points on one base node without edges: one result, the reference's exception text (:345-349)."""
+    base, queries = golden.normalised(oracle)
+    nd = base.shape[0]
+    row_off, nbrs = bipartite_from_knn(golden.z["train_knn_ids"], nd, 12)
+    lonely = int(np.flatnonzero(np.diff(row_off.astype(np.int64))[:nd] == 0)[0])
+    init = np.full((queries.shape[0], 10), lonely, dtype=np.uint32)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_bipartite(row_off, nbrs)
+    with pytest.raises(rg.RgError) as e:
+        idx.search_bipartite(queries, 2, 20, init_ids=init)
+    assert e.value.code == rg.RG_ENOTENOUGH and "not enough results: 1, expected: 2" in str(e.value)
+    ids, dists, cmps, hops = idx.search_bipartite(queries, 1, 20, init_ids=init)
+    assert (ids == lonely).all() and (cmps == 0).all() and (hops == 1).all()
+    idx.close()
+
+
+@pytest.mark.parametrize("R", ["8", "16"])
+def test_merge_insert_equals_one_by_one_insert(oracle, golden, monkeypatch, R):
+    """RG_QUEUE_MERGE=0 (one shift per candidate) and =1 (one merge pass per row group) are observably identical, and
+    both equal the oracle — short queues that overflow inside a group, long ones that never fill."""
+    base, queries = golden.normalised(oracle)
+    monkeypatch.setenv("RG_ROWS_PER_BATCH", R)
+    for L in (10, 13, 40, 700, 2000):
+        want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries, golden.k, L)
+        for merge in ("0", "1"):
+            monkeypatch.setenv("RG_QUEUE_MERGE", merge)
+            idx = rg.RoarIndex(base, golden.metric)
+            idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+            assert_same_search(idx.search(queries, golden.k, L), want, f"merge={merge} R={R} L={L}")
+            idx.close()
+
+
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not available")
 @pytest.mark.parametrize("nb,dim,metric", [(60000, 200, "ip"), (30000, 512, "cosine"), (30000, 96, "l2")])
 def test_live_reference_parity_at_scale(nb, dim, metric):
