@@ -115,6 +115,7 @@ static int fill_params(rg_index *idx, SearchParams &p, uint32_t nq, uint32_t k, 
     p.nq = nq;
     p.k = k;
     p.L = L;
+    idx->last_k = k;
     p.metric_l2 = idx->metric == RG_METRIC_L2 ? 1 : 0;
     p.tag_stride = idx->tag_stride;
     p.counter = idx->d_counter;
@@ -128,7 +129,7 @@ static int check_latched(rg_index *idx) {
     if (st[3] & 1ull) {
         // same text as the reference's runtime_error (src/index_bipartite.cpp:2408-2412)
         char buf[96];
-        snprintf(buf, sizeof(buf), "not enough results: %u, expected: k", (unsigned)(st[3] >> 32));
+        snprintf(buf, sizeof(buf), "not enough results: %u, expected: %u", (unsigned)(st[3] >> 32), idx->last_k);
         set_error(buf);
         return RG_ENOTENOUGH;
     }

@@ -119,6 +119,7 @@ struct rg_index {
     rg::DevBuf<float> q, dists;
     rg::DevBuf<uint32_t> ids, cmps, hops, init;
     rg::SearchLaunch last_launch{};
+    uint32_t last_k = 0;  // k of the last search (for the "not enough results" text)
     cudaStream_t stream = nullptr;  // used by the host-buffer entry points
 };
 
