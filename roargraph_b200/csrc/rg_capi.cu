@@ -367,6 +367,34 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
     p.out_cmps = d_cmps;
     p.out_hops = d_hops;
     SearchLaunch l;
+    // RG_VISITED=smem: the exact hashed visited set (same layout as the L2-resident table below) inside every warp's
+    // shared-memory working set — no DRAM transaction and no DRAM latency for the visited checks, at the price of resident
+    // warps.  Only where a table for ~1.25 x the expected evaluations fits (short queues); else the tag arrays.
+    {
+        const char *vm = getenv("RG_VISITED");
+        if (!bipartite && vm && vm[0] == 's') {
+            uint32_t bits = 1;
+            while (bits < 31 && (1ull << bits) < idx->nd) ++bits;
+            const uint64_t want_entries = (uint64_t)(48.0 * L + 256.0) * 5 / 4;
+            uint32_t bbits = 0;
+            while ((16ull << bbits) < want_entries) ++bbits;
+            if (const char *fb = getenv("RG_VTAB_BBITS")) bbits = (uint32_t)strtoul(fb, nullptr, 10);
+            if (bits > bbits + 14) bbits = bits - 14;
+            if (bbits > bits) bbits = bits;
+            const uint64_t words = 8ull << bbits;
+            if (words * 4 <= (64u << 10)) {
+                p.vt_smem = 1;
+                p.vt_words = (uint32_t)words;
+                p.vt_bbits = bbits;
+                p.vt_rbits = bits - bbits;
+                p.vt_mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+                p.vt_mul = 0x9E3779B1u;
+                uint32_t inv = p.vt_mul;
+                for (int it = 0; it < 5; ++it) inv *= 2u - p.vt_mul * inv;
+                p.vt_mulinv = inv;
+            }
+        }
+    }
     // cudaMemGetInfo (affordable_slots) costs milliseconds and serialises with the device: only ask when this launch wants
     // more slots than already have tag arrays
     rc = plan_search(p, l, g_sm_count, 0xffffffffu);
@@ -383,8 +411,8 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
     p.tags = idx->d_tags;
     p.slot_epoch = idx->d_slot_epoch;
     p.vtab = nullptr;
-    p.vt_words = 0;
-    if (!bipartite) {
+    if (!p.vt_smem) p.vt_words = 0;
+    if (!bipartite && !p.vt_smem) {
         // Visited set of SearchRoarGraph: a per-slot hash table small enough for all slots' tables to stay in L2, so the
         // visited checks stop costing DRAM transactions (the byte-per-node tag array costs one random 32-byte DRAM read and
         // one write-back per examined neighbour: ~25 % of the kernel's DRAM transactions).  Exact: 16-bit entries hold the

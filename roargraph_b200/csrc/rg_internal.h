@@ -56,6 +56,7 @@ struct SearchParams {
     uint32_t *vtab;           // n_slots x vt_words
     uint32_t vt_words;        // 32-bit words per slot (8 per bucket)
     uint32_t vt_bbits, vt_rbits, vt_mask, vt_mul, vt_mulinv;
+    uint32_t vt_smem;         // 1: the table lives in the warp's shared memory (vtab == nullptr, vt_words per warp)
 };
 
 struct SearchLaunch {

@@ -72,6 +72,17 @@ __device__ __forceinline__ void ld_bucket(const uint32_t *p, uint32_t (&v)[8]) {
                  : "l"(p)
                  : "memory");
 }
+// The same bucket in the warp's shared memory (RG_VISITED=smem): two 128-bit shared loads / stores.
+__device__ __forceinline__ void ld_bucket_smem(const uint32_t *p, uint32_t (&v)[8]) {
+    const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <bool kSmem>
+__device__ __forceinline__ void ld_bucket_any(const uint32_t *p, uint32_t (&v)[8]) {
+    if (kSmem) ld_bucket_smem(p, v);
+    else ld_bucket(p, v);
+}
 __device__ __forceinline__ void st_bucket_empty(uint32_t *p) {
     const uint32_t x = 0xffffffffu;
     asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(x) : "memory");
@@ -499,6 +510,7 @@ __device__ __forceinline__ int vt_bucket_insert(uint32_t *bucket, uint32_t (&w)[
 
 // Visited filter on the table: same contract as filter_unvisited_ids; *overflow is set (warp-uniform) when some lane could
 // not record a fresh id (ovf_ids[j] != 0xffffffff names them).
+template <bool kSmem>
 __device__ __forceinline__ uint32_t filter_unvisited_vt(WarpCtx &w, const SearchParams &p, uint32_t *vt, const uint32_t (&id)[3],
                                                         uint32_t cnt, uint32_t ncand, uint32_t (&ovf_ids)[3], bool *overflow) {
     const int lane = w.lane;
@@ -513,7 +525,7 @@ __device__ __forceinline__ uint32_t filter_unvisited_vt(WarpCtx &w, const Search
         bkt[j] = h >> p.vt_rbits;
         rem[j] = h & rmask;
         ovf_ids[j] = 0xffffffffu;
-        if (valid[j]) ld_bucket(vt + (size_t)bkt[j] * 8u, wb[j]);
+        if (valid[j]) ld_bucket_any<kSmem>(vt + (size_t)bkt[j] * 8u, wb[j]);
     }
     bool any_ovf = false;
 #pragma unroll
@@ -524,7 +536,7 @@ __device__ __forceinline__ uint32_t filter_unvisited_vt(WarpCtx &w, const Search
             if (r == 2) {
                 const uint32_t nb = (bkt[j] + 1u) & nb_mask;
                 uint32_t wn[8];
-                ld_bucket(vt + (size_t)nb * 8u, wn);
+                ld_bucket_any<kSmem>(vt + (size_t)nb * 8u, wn);
                 r = vt_bucket_insert(vt + (size_t)nb * 8u, wn, rem[j] | 0x4000u);
                 if (r == 2) {
                     ovf_ids[j] = id[j];  // fresh (in neither bucket) but not recorded
@@ -543,11 +555,12 @@ __device__ __forceinline__ uint32_t filter_unvisited_vt(WarpCtx &w, const Search
 }
 
 // The table is (nearly) full: mark every recorded id in the tag array and carry on with tags for the rest of the query.
+template <bool kSmem>
 __device__ __forceinline__ void vt_migrate(const SearchParams &p, const uint32_t *vt, uint8_t *tags, uint8_t epoch, int lane) {
     const uint32_t nbuckets = 1u << p.vt_bbits, nb_mask = nbuckets - 1u, rmask = (1u << p.vt_rbits) - 1u;
     for (uint32_t b = lane; b < nbuckets; b += 32) {
         uint32_t wv[8];
-        ld_bucket(vt + (size_t)b * 8u, wv);
+        ld_bucket_any<kSmem>(vt + (size_t)b * 8u, wv);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const uint32_t e = (i & 1) ? (wv[i >> 1] >> 16) : (wv[i >> 1] & 0xffffu);
@@ -604,8 +617,14 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
     uint8_t *tags = p.tags + (size_t)slot * p.tag_stride;
     uint32_t epoch = p.slot_epoch[slot];
     constexpr bool use_vt = kVt && kMode == 0;  // hashed visited table (SearchRoarGraph), else the tag array
-    uint32_t *vt = use_vt ? p.vtab + (size_t)slot * p.vt_words : nullptr;
-    w.row_policy = use_vt ? policy_evict_first() : 0ull;
+    // table of this warp: its slice of the L2-resident array, or (RG_VISITED=smem) the tail of its shared-memory working set
+    const bool vt_smem = use_vt && p.vt_smem;
+    uint32_t *vt = nullptr;
+    if (use_vt) {
+        if (vt_smem) vt = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(w.cand + kCandCap) + 31u) & ~(uintptr_t)31u);
+        else vt = p.vtab + (size_t)slot * p.vt_words;
+    }
+    w.row_policy = (use_vt && !vt_smem) ? policy_evict_first() : 0ull;
     // VisitedList::reset (visited_list_pool.h:20-26): bump the tag, clear the array when it wraps
     auto next_epoch = [&]() {
         if (++epoch > 255u) {
@@ -627,7 +646,12 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
 
         bool on_tags = !use_vt;  // a query starts on the table and migrates to the tags only if a bucket pair overflows
         if (use_vt) {
-            for (uint32_t i = (uint32_t)lane * 8u; i < p.vt_words; i += 256u) st_bucket_empty(vt + i);
+            if (vt_smem) {
+                const uint4 e = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                for (uint32_t i = (uint32_t)lane * 4u; i < p.vt_words; i += 128u) *reinterpret_cast<uint4 *>(vt + i) = e;
+            } else {
+                for (uint32_t i = (uint32_t)lane * 8u; i < p.vt_words; i += 256u) st_bucket_empty(vt + i);
+            }
             __syncwarp();
         } else {
             next_epoch();
@@ -637,11 +661,13 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
             if (!use_vt || on_tags) return filter_unvisited_ids(w, tags, (uint8_t)epoch, vid, vcnt, 0, exclude);
             uint32_t ovf_ids[3];
             bool ovf;
-            const uint32_t n = filter_unvisited_vt(w, p, vt, vid, vcnt, 0, ovf_ids, &ovf);
+            const uint32_t n = vt_smem ? filter_unvisited_vt<true>(w, p, vt, vid, vcnt, 0, ovf_ids, &ovf)
+                                       : filter_unvisited_vt<false>(w, p, vt, vid, vcnt, 0, ovf_ids, &ovf);
             if (ovf) {
                 next_epoch();
                 __syncwarp();
-                vt_migrate(p, vt, tags, (uint8_t)epoch, lane);
+                if (vt_smem) vt_migrate<true>(p, vt, tags, (uint8_t)epoch, lane);
+                else vt_migrate<false>(p, vt, tags, (uint8_t)epoch, lane);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                     if (ovf_ids[j] != 0xffffffffu) __stcg(tags + ovf_ids[j], (uint8_t)epoch);
@@ -823,8 +849,9 @@ uint32_t env_u32(const char *name, uint32_t dflt) {
 
 constexpr uint32_t kMaxSmemPerCta = 227u * 1024u;
 
-uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L) {
+uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L, uint32_t vt_bytes = 0) {
     uint32_t b = 64 + dim * 4 + R * rstride * 4 + L * 8 + kCandCap * 4;
+    if (vt_bytes) b += 32 + vt_bytes;  // the shared-memory visited table, 32-byte aligned behind the candidate ids
     return (b + 127u) & ~127u;
 }
 
@@ -861,7 +888,7 @@ int launch_v(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
 
 template <bool kL2, int kMode>
 int launch_t(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
-    if (kMode == 0 && p.vtab) return launch_v<kL2, 0, 4, true>(p, l, s);  // needs the 4-CTA register budget (plan_search caps it)
+    if (kMode == 0 && (p.vtab || p.vt_smem)) return launch_v<kL2, 0, 4, true>(p, l, s);  // needs the 4-CTA register budget
     if (l.warps_per_sm > 24) return launch_v<kL2, kMode, 8>(p, l, s);  // 64 registers
     if (l.warps_per_sm > 16) return launch_v<kL2, kMode, 6>(p, l, s);  // 80
     return launch_v<kL2, kMode, 4>(p, l, s);                           // up to 127
@@ -898,6 +925,7 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     const uint32_t dim = p.dim;
     p.row_stride_smem = dim + ((16u + 32u - (dim & 31u)) & 31u);  // stride % 32 == 16 -> conflict-free float4 reads
     const uint32_t env_warps = env_u32("RG_WARPS_PER_CTA", 0);
+    const uint32_t vt_bytes = p.vt_smem ? p.vt_words * 4u : 0u;
     uint32_t warps = 4, ctas = 0;
     uint32_t R = env_u32("RG_ROWS_PER_BATCH", 0);
     if (R == 0) {
@@ -906,17 +934,17 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
         // (profiles/r1_sweep_10M_ring.csv) it pays when the single-buffered geometry already saturates the memory system
         // (>= 20 warps per SM) or when it keeps at least 72 % of the resident warps.
         uint32_t w8c, c8, w16c, c16;
-        const uint32_t w8 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 8, p.L), env_warps, w8c, c8);
-        const uint32_t w16 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 16, p.L), env_warps, w16c, c16);
+        const uint32_t w8 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 8, p.L, vt_bytes), env_warps, w8c, c8);
+        const uint32_t w16 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 16, p.L, vt_bytes), env_warps, w16c, c16);
         R = (w16 > 0 && (w8 >= 20 || w16 * 100u >= w8 * 72u)) ? 16u : 8u;
     }
     if (R < 8) R = 8;
     if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
     R &= ~7u;
-    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
+    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L, vt_bytes);
     while (wb > kMaxSmemPerCta && R > 8) {
         R -= 8;
-        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L);
+        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L, vt_bytes);
     }
     if (wb > kMaxSmemPerCta) {
         set_error("L_pq / dim too large for one warp's shared-memory working set");

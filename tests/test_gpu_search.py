@@ -117,11 +117,12 @@ def test_device_pointer_entry_and_stats(oracle, golden):
     idx.close()
 
 
+@pytest.mark.parametrize("where", ["hash", "smem"])
 @pytest.mark.parametrize("bbits", [1, 3, 6])
-def test_visited_table_overflow_migrates_to_tags(oracle, golden, monkeypatch, bbits):
-    """The hashed visited table forced tiny (2^bbits buckets of 16 ids): bucket pairs overflow in mid-query and the query
-    migrates to the tag array; ids, distance bits, cmps and hops must not change."""
-    monkeypatch.setenv("RG_VISITED", "hash")
+def test_visited_table_overflow_migrates_to_tags(oracle, golden, monkeypatch, bbits, where):
+    """The hashed visited table (L2-resident or in shared memory) forced tiny (2^bbits buckets of 16 ids): bucket pairs
+    overflow in mid-query and the query migrates to the tag array; ids, distance bits, cmps and hops must not change."""
+    monkeypatch.setenv("RG_VISITED", where)
     monkeypatch.setenv("RG_VTAB_BBITS", str(bbits))
     base, queries = golden.normalised(oracle)
     idx = rg.RoarIndex(base, golden.metric)
@@ -132,7 +133,20 @@ def test_visited_table_overflow_migrates_to_tags(oracle, golden, monkeypatch, bb
     idx.close()
 
 
-@pytest.mark.parametrize("visited", ["tags", "hash"])
+@pytest.mark.parametrize("where", ["hash", "smem"])
+def test_visited_table_default_size_matches_oracle(oracle, golden, monkeypatch, where):
+    """The table at its planned size (no forced overflow): every visited check is answered by the table alone."""
+    monkeypatch.setenv("RG_VISITED", where)
+    base, queries = golden.normalised(oracle)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    for L in (10, 40, 130, 300):
+        want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries, 10, L)
+        assert_same_search(idx.search(queries, 10, L), want, f"{golden.name} visited={where} L={L}")
+    idx.close()
+
+
+@pytest.mark.parametrize("visited", ["tags", "hash", "smem"])
 def test_visited_epoch_wrap(oracle, monkeypatch, visited):
     """> 255 queries through the same warp slot: the 8-bit visited epoch wraps and the tag array is cleared
     (VisitedList::reset, visited_list_pool.h:20-26).  "hash": a 2-bucket visited table, so every query migrates to the
@@ -140,7 +154,7 @@ def test_visited_epoch_wrap(oracle, monkeypatch, visited):
     from conftest import GoldenCase
     g = GoldenCase("ip_d40")
     monkeypatch.setenv("RG_VISITED", visited)
-    if visited == "hash":
+    if visited != "tags":
         monkeypatch.setenv("RG_VTAB_BBITS", "1")
     monkeypatch.setenv("RG_CTAS_PER_SM", "1")
     monkeypatch.setenv("RG_WARPS_PER_CTA", "1")
