@@ -561,20 +561,28 @@ int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, ui
     if (rc != RG_OK) return rc;
     if (!base || !queries || !ids || !dists || nb == 0 || dim == 0) { set_error("rg_knn: null/empty argument"); return RG_EINVAL; }
     if (nq == 0) return RG_OK;
+    // The base goes to HBM once; the queries stream through in batches (the reference walks them 1 024 at a time against
+    // each base part, compute_groundtruth.cpp:187), so device memory is bounded by base + one batch however many queries
+    // there are (10 M x 200 queries + their K = 100 results would otherwise pin 16 GB beside the base).
+    uint64_t batch = 1u << 20;
+    if (const char *hb = getenv("RG_KNN_HOST_BATCH")) batch = std::max<uint64_t>(1, strtoull(hb, nullptr, 10));
+    batch = std::min(batch, nq);
     float *d_b = nullptr, *d_q = nullptr, *d_d = nullptr;
     int32_t *d_i = nullptr;
     cudaError_t e = cudaMalloc(&d_b, nb * dim * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&d_q, nq * dim * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&d_d, nq * K * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&d_i, nq * K * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_q, batch * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, batch * K * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_i, batch * K * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(d_b, base, nb * dim * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice);
     rc = RG_OK;
-    if (e == cudaSuccess) {
-        rc = knn_device(d_b, nb, d_q, nq, dim, K, metric, id_offset, d_i, d_d, nullptr);
+    for (uint64_t q0 = 0; q0 < nq && e == cudaSuccess && rc == RG_OK; q0 += batch) {
+        const uint64_t n = std::min(batch, nq - q0);
+        e = cudaMemcpy(d_q, queries + q0 * dim, n * dim * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        rc = knn_device(d_b, nb, d_q, n, dim, K, metric, id_offset, d_i, d_d, nullptr);
         if (rc == RG_OK) e = cudaDeviceSynchronize();
-        if (rc == RG_OK && e == cudaSuccess) e = cudaMemcpy(ids, d_i, nq * K * sizeof(int32_t), cudaMemcpyDeviceToHost);
-        if (rc == RG_OK && e == cudaSuccess) e = cudaMemcpy(dists, d_d, nq * K * sizeof(float), cudaMemcpyDeviceToHost);
+        if (rc == RG_OK && e == cudaSuccess) e = cudaMemcpy(ids + q0 * K, d_i, n * K * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (rc == RG_OK && e == cudaSuccess) e = cudaMemcpy(dists + q0 * K, d_d, n * K * sizeof(float), cudaMemcpyDeviceToHost);
     }
     if (d_b) cudaFree(d_b);
     if (d_q) cudaFree(d_q);

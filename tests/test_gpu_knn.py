@@ -98,3 +98,16 @@ def test_knn_tensor_core_matches_simt_at_scale(monkeypatch):
         bad = ~same
         assert np.all(np.abs(td[bad] - sd[bad]) <= 1e-4 + 2e-5 * np.abs(sd[bad]))
         assert (np.diff(td, axis=1) >= 0).all()
+
+
+def test_knn_host_entry_streams_query_batches(oracle, monkeypatch):
+    """rg_knn keeps the base resident and streams the queries in batches (ragged last batch): same answer as one batch."""
+    rng = np.random.default_rng(11)
+    base = rng.standard_normal((4000, 72)).astype(np.float32)
+    q = rng.standard_normal((333, 72)).astype(np.float32)
+    whole_i, whole_d = rg.knn(base, q, 20, "l2")
+    monkeypatch.setenv("RG_KNN_HOST_BATCH", "100")
+    part_i, part_d = rg.knn(base, q, 20, "l2")
+    assert (whole_i == part_i).all() and (whole_d.view(np.uint32) == part_d.view(np.uint32)).all()
+    oi, od = oracle.exact_knn(base, q, 20, "l2")
+    check_knn(part_i.astype(np.uint32), part_d, oi.astype(np.uint32), od)
