@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -17,7 +18,17 @@
 #include "cli_args.h"
 #include "rg_b200.h"
 
-static const uint64_t PARTSIZE = 20000000;
+// rows per base part (:32 of the reference); RG_GT_PARTSIZE overrides it (a base that does not fit one GPU beside the
+// query batch, tests)
+static uint64_t part_size() {
+  static const uint64_t v = [] {
+    const char *e = getenv("RG_GT_PARTSIZE");
+    const uint64_t x = e ? strtoull(e, nullptr, 10) : 0;
+    return x ? x : (uint64_t)20000000;
+  }();
+  return v;
+}
+#define PARTSIZE (part_size())
 
 template <typename T>
 static void load_bin_as_float(const std::string &path, std::vector<float> &out, uint64_t &npts, uint64_t &ndims,

@@ -123,6 +123,30 @@ def test_compute_groundtruth_cli_matches_reference_cli(tmp_path, dist_fn):
 
 
 @pytest.mark.gpu
+def test_compute_groundtruth_cli_base_parts_merge(tmp_path):
+    """Base processed in parts (compute_groundtruth.cpp:396-448; 3 parts here, ragged last one): the merged truthset equals
+    the single-part one."""
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((6100, 64)).astype(np.float32)
+    q = rng.standard_normal((150, 64)).astype(np.float32)
+    bf, qf = str(tmp_path / "b.fbin"), str(tmp_path / "q.fbin")
+    F.write_fbin(bf, base)
+    F.write_fbin(qf, q)
+    outs = []
+    for name, env in (("one.gt", {}), ("parts.gt", {"RG_GT_PARTSIZE": "2500"})):
+        gt = str(tmp_path / name)
+        p = subprocess.run([os.path.join(BIN, "compute_groundtruth"), "--data_type", "float", "--dist_fn", "l2", "--base_file",
+                            bf, "--query_file", qf, "--gt_file", gt, "--K", "30"], capture_output=True, text=True,
+                           env={**os.environ, **env})
+        assert p.returncode == 0, p.stdout + p.stderr
+        outs.append((F.read_truthset(gt), p.stdout))
+    ((i1, d1), _), ((i3, d3), out3) = outs
+    assert out3.count("Reading bin file") == 4  # queries + 3 base parts
+    assert (d1.view(np.uint32) == d3.view(np.uint32)).all()
+    assert (i1 == i3).mean() > 0.999  # equal distances may swap
+
+
+@pytest.mark.gpu
 def test_build_cli_then_search_cli(tmp_path, golden):
     import roargraph_b200 as rg
     bf, qf, gf, _ = _write_case(tmp_path, golden)
