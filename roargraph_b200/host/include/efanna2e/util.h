@@ -15,6 +15,9 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#if defined(__SSE__) || defined(__x86_64__)
+#include <xmmintrin.h>
+#endif
 
 namespace efanna2e {
 
@@ -128,10 +131,45 @@ void load_gt_data(const char *filename, uint32_t &points_num, uint32_t &dim, T *
   in.read((char *)data, (std::streamsize)(n * sizeof(T)));
 }
 
-// arr /= ||arr||_2  (float accumulation, like the reference; the last bits of the sum depend on the compiler's
-// reduction order there, so cosine inputs agree with the reference to rounding, not bit for bit)
+// normalize<T> (:214-225 of the reference): x / |x| in place.  The reference's release build (-Ofast -march=native)
+// compiles the loop to 8 lane accumulators with separately rounded multiply and add, the folds (l+4)+l, (l+2)+l, 1+0,
+// RSQRTSS plus one Newton-Raphson step inv = (r*(r*sum) - 3) * (-0.5*r) with the inner product fused, and a MULTIPLY by
+// inv.  For dim % 8 == 0 on x86 this reproduces that sequence (RSQRTSS is executed, not modelled), so cosine inputs reach
+// the device bit-identical to what the reference's loader / CLI hand to its own search; otherwise the source-level
+// arithmetic is used (equal to rounding).
+namespace detail {
+#if defined(__SSE__) || defined(__x86_64__)
+inline bool normalize_as_compiled(float *arr, const size_t dim) {
+  if (dim == 0 || dim % 8 != 0) return false;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t i = 0; i < dim; i += 8)
+    for (size_t l = 0; l < 8; ++l) {
+      volatile float prod = arr[i + l] * arr[i + l];
+      acc[l] = acc[l] + prod;
+    }
+  const float x0 = acc[4] + acc[0], x1 = acc[5] + acc[1], x2 = acc[6] + acc[2], x3 = acc[7] + acc[3];
+  const float y0 = x2 + x0, y1 = x3 + x1;
+  const float sum = y1 + y0;
+  const float rs = _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(sum)));
+  volatile float t = rs * sum;
+  t = std::fmaf(rs, t, -3.0f);
+  const float r2 = rs * -0.5f;
+  const float inv = t * r2;
+  for (size_t i = 0; i < dim; ++i) arr[i] = arr[i] * inv;
+  return true;
+}
+#else
+inline bool normalize_as_compiled(float *, const size_t) { return false; }
+#endif
+template <typename T>
+inline bool normalize_fast(T *, const size_t) { return false; }
+template <>
+inline bool normalize_fast<float>(float *arr, const size_t dim) { return normalize_as_compiled(arr, dim); }
+}  // namespace detail
+
 template <typename T>
 inline void normalize(T *arr, const size_t dim) {
+  if (detail::normalize_fast<T>(arr, dim)) return;
   float sum = 0.0f;
   for (size_t i = 0; i < dim; i++) sum += arr[i] * arr[i];
   sum = std::sqrt(sum);

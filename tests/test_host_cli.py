@@ -88,9 +88,9 @@ def test_search_cli_table_matches_reference_cli(tmp_path, golden):
     to, tr = _table(ours.stdout), _table(ref.stdout)
     assert sorted(to) == sorted(tr) == Ls
     for L in Ls:
-        # avg_cmps, recall, avg_hops are deterministic functions of the results: equal to print precision.
-        # (cosine: host normalisation agrees with the reference's vectorised loop to rounding only, so allow 1e-3)
-        tol = 1e-3 if golden.metric == "cosine" else 1e-6
+        # avg_cmps, recall, avg_hops are deterministic functions of the results: equal to print precision
+        # (cosine included: the mirror's normalize reproduces the reference's compiled loop bit for bit)
+        tol = 1e-6
         assert to[L][1] == pytest.approx(tr[L][1], rel=tol), (L, to[L], tr[L])
         assert to[L][3] == pytest.approx(tr[L][3], abs=tol + 1e-6)
         assert to[L][4] == pytest.approx(tr[L][4], rel=tol)
@@ -326,7 +326,7 @@ def test_reference_search_main_on_the_mirror_prints_the_reference_table(tmp_path
     assert ref.returncode == 0, ref.stderr
     to, tr = _table(ours.stdout), _table(ref.stdout)
     assert sorted(to) == sorted(tr) == Ls
-    tol = 1e-3 if golden.metric == "cosine" else 1e-6
+    tol = 1e-6
     for L in Ls:
         assert to[L][1] == pytest.approx(tr[L][1], rel=tol), (L, to[L], tr[L])   # avg cmps
         assert to[L][3] == pytest.approx(tr[L][3], abs=tol + 1e-6)                # recall

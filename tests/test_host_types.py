@@ -30,6 +30,23 @@ def test_neighbor_priority_queue_mirror_traces_equal_reference(tmp_path):
         assert a == b and a.count("\n") > 3, (cap, n_ops, id_range, seed)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_INC, "efanna2e", "util.h")), reason="/root/reference not mounted")
+def test_normalize_mirror_is_bit_identical_to_the_compiled_reference(tmp_path):
+    """efanna2e::normalize as the reference's release flags compile it (8 lane sums, RSQRTSS + one Newton step, multiply)
+    vs the mirror's restatement of that instruction sequence, dim % 8 == 0 (the reference's own precondition for cosine,
+    SURVEY.md 9.10): identical bits.  This is what makes the cosine CLI path feed the device the reference's exact rows."""
+    driver = os.path.join(ROOT, "tests", "cpp", "normalize_driver.cpp")
+    ref, ours = str(tmp_path / "norm_ref"), str(tmp_path / "norm_ours")
+    # the reference's flags (CMakeLists.txt:28) / the mirror's (roargraph_b200/host/Makefile)
+    subprocess.check_call(["g++", "-std=c++17", "-Ofast", "-DNDEBUG", "-march=native", "-mtune=native", "-ftree-vectorize",
+                           "-w", "-I", REF_INC, driver, "-o", ref])
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-I", MIRROR_INC, driver, "-o", ours])
+    for dim, rows, seed in ((8, 50, 1), (64, 200, 2), (200, 300, 3), (512, 100, 4), (104, 64, 5)):
+        a = subprocess.run([ref, str(dim), str(rows), str(seed)], capture_output=True, text=True, check=True).stdout
+        b = subprocess.run([ours, str(dim), str(rows), str(seed)], capture_output=True, text=True, check=True).stdout
+        assert a == b and len(a) > dim * rows * 8, (dim, rows, seed)
+
+
 def test_mirror_headers_are_self_contained(tmp_path):
     """Every public header of the mirror compiles on its own (what a maintainer's include-path switch relies on)."""
     for h in ("efanna2e/distance.h", "efanna2e/neighbor.h", "efanna2e/parameters.h", "efanna2e/util.h", "efanna2e/index.h",

@@ -63,3 +63,12 @@ def test_not_enough_results(oracle, golden):
     row_off = np.zeros(nd + 1, dtype=np.uint64)  # graph without edges: only the entry point is found
     r = oracle.search_roargraph(base, row_off, np.zeros(0, np.uint32), 0, golden.metric, queries[:4], 5, 8, 1)
     assert r["nfail"] == 4 and (r["status"] == -2).all()
+
+
+def test_normalised_rows_of_the_cosine_fixture(oracle):
+    """The rows the reference's loader / CLI produced for the cosine fixture (stored by make_golden.py) are reproduced
+    bit for bit by the oracle's normalize restatement."""
+    from conftest import GoldenCase
+    g = GoldenCase("cos_d64")
+    assert (oracle.normalize_rows(g.base.copy()).view(np.uint32) == g.z["base_norm"].view(np.uint32)).all()
+    assert (oracle.normalize_rows(g.queries.copy()).view(np.uint32) == g.z["queries_norm"].view(np.uint32)).all()

@@ -23,9 +23,13 @@ def test_distance_random(oracle):
 def test_normalize_matches(oracle):
     from oracle.oracle import Reference
     R = Reference()
-    x = np.random.default_rng(5).standard_normal((50, 64)).astype(np.float32)
-    # the reference's loop is auto-vectorised under -Ofast (different summation order): equal to rounding only
-    np.testing.assert_allclose(R.normalize_rows(x), oracle.normalize_rows(x), rtol=2e-6, atol=1e-7)
+    rng = np.random.default_rng(5)
+    for dim in (8, 64, 104, 200, 512):
+        x = (rng.standard_normal((300, dim)) * rng.uniform(0.01, 100.0, (300, 1))).astype(np.float32)
+        # the restatement follows the COMPILED loop (lane sums, RSQRTSS + Newton step, multiply): bit for bit
+        assert (R.normalize_rows(x.copy()).view(np.uint32) == oracle.normalize_rows(x.copy()).view(np.uint32)).all(), dim
+    x = rng.standard_normal((50, 13)).astype(np.float32)  # dim % 8 != 0: outside the reference's precondition, rounding only
+    np.testing.assert_allclose(R.normalize_rows(x.copy()), oracle.normalize_rows(x.copy()), rtol=2e-6, atol=1e-7)
 
 
 def test_search_live_reference(oracle, golden, tmp_path):
