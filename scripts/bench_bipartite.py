@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""SearchBipartiteGraph at the size of BASELINE.json configs[1]: 10 M x 200 base, 1 M training queries,
+raw bipartite graph of qbaseNNbipartite (src/index_bipartite.cpp:235-280, M_pjbp = 35), 10 000 test queries, top-10, ten
+seeded entry points per query.  Prints one JSON line: the L_pq sweep (QPS through the host-buffer C-ABI call, recall@10,
+avg cmps / hops, gather GB/s) — the paper's weak baseline beside RoarGraph's own numbers in profiles/r1_sweep_10M.csv.
+
+    python scripts/bench_bipartite.py [--nb 10000000] [--out gpurun_out/bipartite_10M.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def bipartite_csr(knn_ids: np.ndarray, nd: int, M_pjbp: int):
+    """Vectorised qbaseNNbipartite: query node nd + sq -> its first M_pjbp NNs except (every occurrence of) the top-1;
+    base node top-1(sq) -> nd + sq, in ascending sq (the reference's single-thread order)."""
+    nn = np.ascontiguousarray(knn_ids[:, :M_pjbp]).astype(np.uint32)
+    nsq = nn.shape[0]
+    tgt = nn[:, 0]
+    keep = nn != tgt[:, None]
+    q_deg = keep.sum(1)
+    order = np.argsort(tgt, kind="stable")
+    b_deg = np.bincount(tgt, minlength=nd)
+    row_off = np.zeros(nd + nsq + 1, dtype=np.uint64)
+    row_off[1:nd + 1] = np.cumsum(b_deg)
+    row_off[nd + 1:] = row_off[nd] + np.cumsum(q_deg).astype(np.uint64)
+    nbrs = np.concatenate([(order + nd).astype(np.uint32), nn[keep]])
+    return row_off, nbrs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nb", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=200)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--M_pjbp", type=int, default=35)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    import torch
+
+    import roargraph_b200 as rg
+    from roargraph_b200 import synth
+    from roargraph_b200.workload import recall_at_k, log
+
+    rg.init(0)
+    dev = torch.device("cuda", 0)
+    ntrain, k = max(1000, a.nb // 10), 10
+    base, train, test = synth.make_torch(a.nb, ntrain, a.nq, a.dim, dev, seed=1234)
+    gt_i = torch.empty((a.nq, k), dtype=torch.int32, device=dev)
+    gt_d = torch.empty((a.nq, k), dtype=torch.float32, device=dev)
+    rg.knn_dev(base, test, k, "ip", gt_i, gt_d)
+    kn_i = torch.empty((ntrain, a.M_pjbp), dtype=torch.int32, device=dev)
+    kn_d = torch.empty((ntrain, a.M_pjbp), dtype=torch.float32, device=dev)
+    t0 = time.time()
+    rg.knn_dev(base, train, a.M_pjbp, "ip", kn_i, kn_d)
+    torch.cuda.synchronize()
+    log(f"training-query kNN: {time.time() - t0:.1f}s")
+    gt = gt_i.cpu().numpy().astype(np.uint32)
+    t0 = time.time()
+    row_off, nbrs = bipartite_csr(kn_i.cpu().numpy().view(np.uint32), a.nb, a.M_pjbp)
+    log(f"bipartite graph on the host: {time.time() - t0:.1f}s, {len(nbrs)} edges, "
+        f"{(np.diff(row_off[:a.nb + 1].astype(np.int64)) > 0).mean():.3f} of the base nodes have out-edges")
+    del kn_i, kn_d, train
+    rg.knn_release_workspace()
+    idx = rg.RoarIndex(base, "ip")
+    idx.set_bipartite(row_off, nbrs)
+    q = test.cpu().numpy()
+    rows = []
+    for L in (10, 20, 50, 100, 200, 500, 1000):
+        idx.search_bipartite(q[:100], k, L, seed=7)  # the CLI's warm-up
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ids, d, cmps, hops = idx.search_bipartite(q, k, L, seed=7)
+            ts.append(time.perf_counter() - t0)
+        st = idx.last_stats()
+        sec = min(ts)
+        rows.append({"L_pq": L, "qps": a.nq / sec, "recall": recall_at_k(ids, gt, k), "avg_cmps": float(cmps.mean()),
+                     "avg_hops": float(hops.mean()), "gather_GBps": (st["cmps"] + a.nq * 10) * a.dim * 4 / sec / 1e9})
+        log(str(rows[-1]))
+    line = {"path": "SearchBipartiteGraph (A2)", "workload": f"{a.nb}x{a.dim} ip, {ntrain} training queries, M_pjbp={a.M_pjbp}, "
+            f"{a.nq} queries top-{k}, 10 seeded entry points", "timing": "wall clock of rg_search_bipartite (host buffers: H2D + "
+            "kernel + D2H), best of 3", "sweep": rows}
+    print(json.dumps(line), flush=True)
+    if a.out:
+        os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+        with open(a.out, "w") as f:
+            f.write(json.dumps(line) + "\n")
+
+
+if __name__ == "__main__":
+    main()
