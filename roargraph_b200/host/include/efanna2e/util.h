@@ -6,6 +6,7 @@
 // of 8 is handled consistently (the reference's data_align re-reads already padded rows with the unpadded stride,
 // which is only correct when dim % 8 == 0 — SURVEY.md 9.10).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #if defined(__SSE__) || defined(__x86_64__)
 #include <xmmintrin.h>
@@ -174,6 +176,24 @@ inline void normalize(T *arr, const size_t dim) {
   for (size_t i = 0; i < dim; i++) sum += arr[i] * arr[i];
   sum = std::sqrt(sum);
   for (size_t i = 0; i < dim; i++) arr[i] = (T)(arr[i] / sum);
+}
+
+// normalize() over n rows of stride `dim` on `threads` host threads (0 = all cores); every row is independent, so the
+// result does not depend on the thread count.  The reference runs this loop serially at load time
+// (src/index_bipartite.cpp:2679-2684): 10 M x 512 rows take it ~10 s.
+inline void normalize_rows(float *rows, size_t n, size_t dim, unsigned threads = 0) {
+  if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+  threads = (unsigned)std::min<size_t>(threads, std::max<size_t>(1, n / 4096));
+  if (threads <= 1) {
+    for (size_t i = 0; i < n; ++i) normalize<float>(rows + i * dim, dim);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([=] {
+      for (size_t i = n * t / threads, e = n * (t + 1) / threads; i < e; ++i) normalize<float>(rows + i * dim, dim);
+    });
+  for (auto &th : pool) th.join();
 }
 
 }  // namespace efanna2e

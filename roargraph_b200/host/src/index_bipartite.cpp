@@ -97,7 +97,7 @@ void IndexBipartite::LoadVectorData(const char *base_file, const char *sampled_q
   }
   if (need_normalize) {
     std::cout << "Normalizing base data" << std::endl;
-    for (size_t i = 0; i < base_num; ++i) normalize<float>(base + i * (uint64_t)padded, padded);
+    normalize_rows(base, base_num, padded);
   }
   free(owned_base_);
   owned_base_ = base;
@@ -211,8 +211,7 @@ void IndexBipartite::BuildBipartite(size_t n_sq, const float *sq_data, size_t n_
   if (n_bp + n_sq > 0xffffffffull) throw std::invalid_argument("more than 2^32 nodes");
   if (need_normalize && bp_data) {
     std::cout << "normalizing base data" << std::endl;
-    float *d = const_cast<float *>(bp_data);
-    for (size_t i = 0; i < n_bp; ++i) normalize(d + i * dimension_, dimension_);
+    normalize_rows(const_cast<float *>(bp_data), n_bp, dimension_);
   }
   nd_sq_ = n_sq;
   // the graph is assembled on the host; the base goes to HBM with the first search (a build-only run needs no GPU)
@@ -290,8 +289,7 @@ void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_
   if (learn_base_knn_.empty()) throw std::runtime_error("LoadLearnBaseKNN must be called before BuildRoarGraph");
   if (need_normalize) {
     std::cout << "normalizing base data" << std::endl;
-    float *d = const_cast<float *>(bp_data);
-    for (size_t i = 0; i < n_bp; ++i) normalize(d + i * dimension_, dimension_);
+    normalize_rows(const_cast<float *>(bp_data), n_bp, dimension_);
   }
   nd_sq_ = n_sq;
   if (dimension_ % 8 != 0) {

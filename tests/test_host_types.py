@@ -47,6 +47,32 @@ def test_normalize_mirror_is_bit_identical_to_the_compiled_reference(tmp_path):
         assert a == b and len(a) > dim * rows * 8, (dim, rows, seed)
 
 
+def test_normalize_rows_is_thread_count_independent(tmp_path):
+    src = tmp_path / "nr.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "efanna2e/util.h"
+int main() {
+  const size_t n = 50000, dim = 40;
+  std::vector<float> a(n * dim), b;
+  for (size_t i = 0; i < a.size(); ++i) a[i] = (float)((i * 2654435761u) % 1000) / 37.0f - 13.0f;
+  b = a;
+  efanna2e::normalize_rows(a.data(), n, dim, 1);
+  efanna2e::normalize_rows(b.data(), n, dim, 7);
+  std::vector<float> c(a.size());
+  for (size_t i = 0; i < a.size(); ++i) c[i] = (float)((i * 2654435761u) % 1000) / 37.0f - 13.0f;
+  for (size_t r = 0; r < n; ++r) efanna2e::normalize<float>(c.data() + r * dim, dim);
+  printf("%d %d\n", memcmp(a.data(), b.data(), a.size() * 4), memcmp(a.data(), c.data(), a.size() * 4));
+  return 0;
+}
+""")
+    exe = str(tmp_path / "nr")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I", MIRROR_INC, str(src), "-o", exe])
+    assert subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split() == ["0", "0"]
+
+
 def test_mirror_headers_are_self_contained(tmp_path):
     """Every public header of the mirror compiles on its own (what a maintainer's include-path switch relies on)."""
     for h in ("efanna2e/distance.h", "efanna2e/neighbor.h", "efanna2e/parameters.h", "efanna2e/util.h", "efanna2e/index.h",
