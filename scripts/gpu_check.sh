@@ -9,9 +9,10 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
 nproc >> $OUT/gpu_$TAG.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> $OUT/gpu_$TAG.txt
 if [ "$TESTS" != "none" ]; then
-  timeout 1500 python -m pytest $TESTS -x -q -m gpu > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_$TAG.log
+  timeout 1500 python -m pytest $TESTS -q -m gpu > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_$TAG.log
   tail -5 $OUT/pytest_$TAG.log
 fi
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke_$TAG.log
 timeout 1200 python bench.py --nb $NB --steps 20 --warmup 3 --sweep $OUT/sweep_$TAG.csv > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 tail -3 $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json
 L=$(python -c "import json;print(json.loads(open('$OUT/bench_$TAG.json').read().strip().splitlines()[-1])['config']['L_pq'])" 2>/dev/null || echo 50)
