@@ -960,6 +960,15 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     uint32_t grid = (uint32_t)sm_count * ctas;
     const uint32_t need = (p.nq + warps - 1) / warps;
     if (grid > need) grid = need;
+    if (env_u32("RG_WAVE_FIT", 0) && (uint64_t)grid * warps < p.nq) {
+        // opt-in: trim the grid so that the batch is a whole number of waves (10 000 queries on 2 072 slots = 4.83 waves ->
+        // 2 000 slots, 5.0 waves): the last wave then ends together instead of leaving 17 % of the slots idle for a query's
+        // duration.  Dynamic tickets already balance most of it; measured before it becomes the default.
+        const uint32_t slots = grid * warps;
+        const uint32_t waves = (p.nq + slots - 1) / slots;
+        const uint32_t fit = (p.nq + waves - 1) / waves;
+        grid = std::max(1u, std::min(grid, (fit + warps - 1) / warps));
+    }
     if (grid * warps > max_slots) grid = max_slots / warps;
     if (grid < 1) grid = 1;
     p.rows_per_batch = R;
