@@ -1,4 +1,6 @@
 """CPU: file formats of the reference round-trip and decode the reference-written index bytes."""
+import os
+
 import numpy as np
 
 from conftest import GoldenCase
@@ -38,3 +40,30 @@ def test_recall():
     res = np.array([[1, 2, 3], [4, 5, 6]], dtype=np.uint32)
     gt = np.array([[3, 2, 9, 1], [7, 8, 9, 4]], dtype=np.uint32)
     assert abs(F.compute_recall(res, gt, 3) - 2 / 6) < 1e-9
+
+
+def test_ragged_graph_files_roundtrip_property(tmp_path):
+    """Random ragged adjacency (empty rows, an all-empty graph, one long row) through both index file formats."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=9), min_size=1, max_size=40), st.integers(0, 2**31 - 1))
+    def check(degs, seed):
+        rng = np.random.default_rng(seed)
+        degs = np.array(degs, dtype=np.int64)
+        if seed % 5 == 0:
+            degs[seed % len(degs)] = 300  # one long row
+        ro = np.zeros(len(degs) + 1, dtype=np.uint64)
+        ro[1:] = np.cumsum(degs)
+        nb = rng.integers(0, len(degs), int(ro[-1])).astype(np.uint32)
+        ep = int(seed % len(degs))
+        p = str(tmp_path / "g.rg")
+        F.write_projection_index(p, ep, ro, nb)
+        assert os.path.getsize(p) == 4 * (2 + len(degs) + len(nb))
+        ep2, ro2, nb2 = F.read_projection_index(p)
+        assert ep2 == ep and (ro2 == ro).all() and (nb2 == nb).all()
+        F.write_bipartite_index(p, ro, nb)
+        ro3, nb3 = F.read_bipartite_index(p)
+        assert (ro3 == ro).all() and (nb3 == nb).all()
+
+    check()
