@@ -146,13 +146,13 @@ def load_tensor_peak(burst=False):
     return (1650.0 if burst else 1400.0), "fallback (B200_PROFILING.md, " + ("burst)" if burst else "sustained)")
 
 
-def time_knn(a, w, dev, world, K=100, reps=2):
+def time_knn(a, w, dev, world, K=100, reps=2, query_sharded=False):
     """BASELINE.json's second metric: brute-force training-query x base kNN pairs/s (compute_groundtruth's exact_knn),
     base sharded over the ranks like the search (configs[3]): local tcgen05 filter + exact re-rank, all-gather, merge."""
     import torch
     import torch.distributed as dist
 
-    from roargraph_b200.sharded import sharded_knn_dev
+    from roargraph_b200.sharded import query_sharded_knn_dev, sharded_knn_dev
 
     q = w.d_train_sample
     metric = "l2" if a.dist == "l2" else "ip"
@@ -162,7 +162,10 @@ def time_knn(a, w, dev, world, K=100, reps=2):
             dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        ids, dists = sharded_knn_dev(w.d_base, q, K, metric, w.row_lo)
+        if query_sharded:  # replicas: every rank holds the whole base and scores its slice of the queries
+            ids, dists = query_sharded_knn_dev(w.d_base, q, K, metric)
+        else:
+            ids, dists = sharded_knn_dev(w.d_base, q, K, metric, w.row_lo)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if world > 1:
@@ -182,7 +185,8 @@ def time_knn(a, w, dev, world, K=100, reps=2):
                          "peak_burst": burst * world, "frac_of_burst": tf / (burst * world),
                          "kernel": "knn_tc_filter_pair_kernel (tcgen05 bf16 filter) + knn_merge_fast_kernel (fp32 re-rank)"},
             "note": "wall clock of the whole call: fp32->bf16 conversion, norms, every filter and merge launch"
-                    + (", all-gather + k-way merge over the shards" if world > 1 else "")}
+                    + ((", queries split over the ranks, all-gather of the result blocks" if query_sharded else
+                        ", all-gather + k-way merge over the shards") if world > 1 else "")}
 
 
 def time_reference_cpu(a, w, L, steps, warmup, budget_s):
@@ -454,9 +458,9 @@ def main():
         sweep_table = a.sweep
 
     knn_out = None
-    if not a.no_knn and not replicas:  # the kNN leg shards the BASE (configs[3]); replicas hold all of it
+    if not a.no_knn:  # base-sharded like the search (configs[3]); with --shard query the queries are split instead
         try:
-            knn_out = time_knn(a, w, dev, world)
+            knn_out = time_knn(a, w, dev, world, query_sharded=replicas)
         except Exception as e:  # noqa: BLE001
             knn_out = {"error": repr(e)}
 

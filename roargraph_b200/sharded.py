@@ -209,3 +209,36 @@ def sharded_knn_dev(d_base_shard, d_queries, K: int, metric, row_lo: int, group=
         all_d, all_i = gather_topk(loc_d[lo:hi], loc_i[lo:hi], group)
         merge(all_d, all_i, out_d[lo:hi], out_i[lo:hi])
     return out_i, out_d
+
+
+def query_sharded_knn_dev(d_base_full, d_queries, K: int, metric, group=None, local_knn=None):
+    """Brute-force kNN with the QUERIES sharded and the base replicated — the comparison point SURVEY.md 8(e) names for
+    the base-sharded contract above: rank r scores queries [r * per, (r + 1) * per) against ALL base rows and one
+    all-gather collects the per-rank result blocks; no merge step, and every rank's tensor-core filter streams the whole
+    base (the base-sharded form runs G times as many, G times smaller filter passes).  Needs the full base on every GPU.
+
+    Returns (ids int32 [nq, K], dists fp32 [nq, K]) on the device, complete on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    nq = d_queries.shape[0]
+    dev = d_queries.device
+    if local_knn is None:
+        def local_knn(b, q, k, m, ids, dists, id_offset):
+            rg.knn_dev(b, q, k, m, ids, dists, id_offset=id_offset, stream=torch.cuda.current_stream())
+    per = -(-nq // world)
+    lo = min(rank * per, nq)
+    hi = min(lo + per, nq)
+    loc_i = torch.zeros((per, K), dtype=torch.int32, device=dev)
+    loc_d = torch.zeros((per, K), dtype=torch.float32, device=dev)
+    if hi > lo:
+        local_knn(d_base_full, d_queries[lo:hi], K, metric, loc_i[:hi - lo], loc_d[:hi - lo], 0)
+    if world == 1:
+        return loc_i[:nq], loc_d[:nq]
+    all_i = torch.empty((world * per, K), dtype=torch.int32, device=dev)
+    all_d = torch.empty((world * per, K), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(all_i, loc_i, group=group)
+    dist.all_gather_into_tensor(all_d, loc_d, group=group)
+    return all_i[:nq], all_d[:nq]  # rank r's block starts at r * per: query order, padding only behind the last query

@@ -151,3 +151,37 @@ def test_two_rank_query_sharded_replicas(tmp_path, oracle, nq):
     want = oracle.search_roargraph(g.base, g.row_off, g.nbrs, g.ep, g.metric, g.queries[:nq], 10, 32)
     assert (z["i"].view(np.uint32) == want["ids"]).all()
     assert (z["d"].view(np.uint32) == want["dists"].view(np.uint32)).all()
+
+
+def _qknn_worker(rank, world, port, out, nq):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    from roargraph_b200.sharded import query_sharded_knn_dev
+    O = Oracle()
+    g = GoldenCase("l2_d104")
+    K = 9
+
+    def local_knn(b, q, k, m, ids, dists, id_offset):  # checker standing in for rg.knn_dev
+        i, d = O.exact_knn(b.numpy(), q.numpy(), k, m)
+        ids.copy_(torch.from_numpy(i.astype(np.int32) + id_offset))
+        dists.copy_(torch.from_numpy(d))
+
+    ids, dists = query_sharded_knn_dev(torch.from_numpy(g.base_raw), torch.from_numpy(g.test_raw[:nq]), K, "l2",
+                                       local_knn=local_knn)
+    assert ids.shape == (nq, K)
+    if rank == 0:
+        np.savez(out, d=dists.numpy(), i=ids.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [48, 35, 1])
+def test_two_rank_query_sharded_knn(tmp_path, oracle, nq):
+    """Queries split over two ranks (ragged, and a rank with nothing to do), base replicated: equals the one-process kNN."""
+    out = str(tmp_path / "qknn.npz")
+    mp.spawn(_qknn_worker, args=(2, _free_port(), out, nq), nprocs=2, join=True)
+    z = np.load(out)
+    g = GoldenCase("l2_d104")
+    full_i, full_d = oracle.exact_knn(g.base_raw, g.test_raw[:nq], 9, "l2")
+    assert (z["i"] == full_i).all() and (z["d"].view(np.uint32) == full_d.view(np.uint32)).all()
