@@ -15,7 +15,7 @@ namespace cli {
 struct Option {
   std::string name, help;
   char short_name = 0;
-  bool required = false, multitoken = false, seen = false, has_default = false;
+  bool required = false, multitoken = false, seen = false, has_default = false, numeric = false;
   std::vector<std::string> values;
 };
 
@@ -36,6 +36,13 @@ class Parser {
       o.has_default = true;
     }
     opts_.push_back(o);
+    return *this;
+  }
+
+  // marks the option added last as an unsigned integer: parse() then rejects other values, where
+  // boost::program_options rejects them (inside the CLI's try block: message on stderr, exit code -1)
+  Parser &numeric() {
+    if (!opts_.empty()) opts_.back().numeric = true;
     return *this;
   }
 
@@ -65,6 +72,8 @@ class Parser {
     for (auto &o : opts_) {
       if (o.seen && o.values.empty()) throw std::runtime_error("the required argument for option '--" + o.name + "' is missing");
       if (o.required && !o.seen && !o.has_default) throw std::runtime_error("the option '--" + o.name + "' is required but missing");
+      if (o.numeric)
+        for (auto &v : o.values) (void)to_u64(o.name, v);
     }
     return 0;
   }

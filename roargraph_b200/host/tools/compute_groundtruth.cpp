@@ -134,7 +134,7 @@ int main(int argc, char **argv) {
       .add("base_file", "File containing the base vectors in binary format", true)
       .add("query_file", "File containing the query vectors in binary format", true)
       .add("gt_file", "File name for the writing ground truth in binary format", true)
-      .add("K", "Number of ground truth nearest neighbors to compute", true)
+      .add("K", "Number of ground truth nearest neighbors to compute", true).numeric()
       .add("tags_file", "File containing the tags in binary format", false);
   try {
     if (args.parse(argc, argv)) return 0;

@@ -16,12 +16,12 @@ int main(int argc, char **argv) {
       .add("sampled_query_data_path", "Sampled query file in bin format", true)
       .add("projection_index_save_path", "Path prefix for saving projetion index file components", true)
       .add("learn_base_nn_path", "Path of learn-base NN file", true)
-      .add("M_sq", "Number of neighbors for sampled query points to build the bipartite graph", false, false, "32")
-      .add("M_pjbp", "Number of neighbors for projection graph", false, false, "32")
-      .add("L_pjpq", "Priority queue length for projection graph searching", false, false, "32")
-      .add("build_rounds", "bulk-synchronous rounds of the connectivity phase (0 = automatic)", false, false, "0")
+      .add("M_sq", "Number of neighbors for sampled query points to build the bipartite graph", false, false, "32").numeric()
+      .add("M_pjbp", "Number of neighbors for projection graph", false, false, "32").numeric()
+      .add("L_pjpq", "Priority queue length for projection graph searching", false, false, "32").numeric()
+      .add("build_rounds", "bulk-synchronous rounds of the connectivity phase (0 = automatic)", false, false, "0").numeric()
       .add("num_threads", "Number of host threads (kept for compatibility; the build runs on the GPU)", false, false,
-           std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T');
+           std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T').numeric();
   try {
     if (args.parse(argc, argv)) return 0;
   } catch (const std::exception &ex) {

@@ -19,13 +19,13 @@ int main(int argc, char **argv) {
       .add("sampled_query_data_path", "Sampled query file in bin format", true)
       .add("bipartite_index_save_path", "Path prefix for saving bipartite index file components", true)
       .add("projection_index_save_path", "Path prefix for saving projetion index file components", true)
-      .add("M_bp", "Number of neighbors for base points to build the bipartite graph", false, false, "32")
-      .add("M_sq", "Number of neighbors for sampled query points to build the bipartite graph", false, false, "32")
-      .add("M_pjbp", "Number of neighbors for projection graph", false, false, "32")
-      .add("L_pjpq", "Priority queue length for projection graph searching", false, false, "32")
-      .add("L_pq", "Priority queue length for searching", false, false, "32")
+      .add("M_bp", "Number of neighbors for base points to build the bipartite graph", false, false, "32").numeric()
+      .add("M_sq", "Number of neighbors for sampled query points to build the bipartite graph", false, false, "32").numeric()
+      .add("M_pjbp", "Number of neighbors for projection graph", false, false, "32").numeric()
+      .add("L_pjpq", "Priority queue length for projection graph searching", false, false, "32").numeric()
+      .add("L_pq", "Priority queue length for searching", false, false, "32").numeric()
       .add("num_threads", "Number of host threads (kept for compatibility)", false, false,
-           std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T')
+           std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T').numeric()
       .add("learn_base_nn_path", "Path of learn-base NN file", true)
       .add("base_learn_nn_path", "Path of base-learn NN file", true);
   try {

@@ -32,11 +32,11 @@ int main(int argc, char **argv) {
       .add("query_path", "Query file in bin format", true)
       .add("gt_path", "Groundtruth file in bin format", true)
       .add("projection_index_save_path", "Path prefix for saving projetion index file components", true)
-      .add("L_pq", "Priority queue length for searching", true, true)
-      .add("k", "k nearest neighbors", true, false, "1")
+      .add("L_pq", "Priority queue length for searching", true, true).numeric()
+      .add("k", "k nearest neighbors", true, false, "1").numeric()
       .add("evaluation_save_path", "Path prefix for saving evaluation results", false)
       .add("num_threads", "Number of host threads (kept for compatibility; the search runs on the GPU)", false, false,
-           std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T');
+           std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T').numeric();
   try {
     if (args.parse(argc, argv)) return 0;
   } catch (const std::exception &ex) {

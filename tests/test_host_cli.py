@@ -32,6 +32,17 @@ def test_help_and_missing_arguments():
         assert p.returncode == 255 and "required but missing" in p.stderr  # the reference returns -1 (:114-117)
     p = run("test_search_roargraph", "--bogus", "1")
     assert p.returncode == 255 and "unrecognised option" in p.stderr
+    # boost::program_options behaviours the reference's scripts rely on: multitoken --L_pq, -T alias, value validation
+    common = ["--data_type", "float", "--dist", "ip", "--base_data_path", "/nonexistent/b", "--query_path", "/nonexistent/q",
+              "--gt_path", "/nonexistent/g", "--projection_index_save_path", "/nonexistent/i"]
+    p = run("test_search_roargraph", *common, "--L_pq", "10", "x20", "--k", "10")
+    assert p.returncode == 255 and "is invalid" in p.stderr
+    p = run("test_search_roargraph", *common, "--L_pq", "10", "20", "--k")
+    assert p.returncode == 255 and "required argument" in p.stderr
+    p = run("test_search_roargraph", "stray", *common, "--L_pq", "10")
+    assert p.returncode == 255 and "positional" in p.stderr
+    p = run("test_search_roargraph", *common, "--L_pq", "10", "20", "30", "-T", "3", "--k", "10")
+    assert p.returncode != 0 and "open file error" in (p.stdout + p.stderr)  # parsed fine; the loader exits like the reference's
 
 
 def _write_case(tmp_path, golden):
