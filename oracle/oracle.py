@@ -5,6 +5,8 @@ module.  Nothing under roargraph_b200/ imports it (tests/test_no_oracle_in_produ
 
 * ``Oracle``    -> oracle/liboracle.so        (plain-C restatement, oracle/roar_oracle.c)
 * ``Reference`` -> oracle/_ref/libref_roargraph.so (the reference's own code compiled unmodified, oracle/ref_capi.cpp)
+* ``Reference(detrand=True)`` -> oracle/_ref/libref_roargraph_detrand.so: the same translation units with
+  oracle/shims/fixed_random_device.h pre-included, so that SearchBipartiteGraph's entry points are reproducible
 """
 from __future__ import annotations
 
@@ -30,6 +32,10 @@ def build(ref: bool = True) -> None:
 
 def have_reference() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libref_roargraph.so"))
+
+
+def have_detrand_reference() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_roargraph_detrand.so"))
 
 
 class Oracle:
@@ -111,12 +117,20 @@ class Oracle:
 class Reference:
     """The unmodified reference (prebuilt oracle/_ref/libref_roargraph.so; built from /root/reference when present)."""
 
-    def __init__(self):
-        path = os.path.join(HERE, "_ref", "libref_roargraph.so")
+    def __init__(self, detrand: bool = False):
+        path = os.path.join(HERE, "_ref", "libref_roargraph_detrand.so" if detrand else "libref_roargraph.so")
         if not os.path.exists(path):
-            raise RuntimeError("oracle/_ref/libref_roargraph.so missing: run `make -C oracle ref` where "
-                               "/root/reference is mounted")
+            raise RuntimeError(f"{path} missing: run `make -C oracle ref` where /root/reference is mounted")
         self.lib = L = C.CDLL(path)
+        self.detrand = detrand
+        L.ref_has_fixed_random_device.restype = C.c_int
+        assert bool(L.ref_has_fixed_random_device()) == detrand
+        L.ref_bipartite_load.restype = C.c_void_p
+        L.ref_bipartite_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_uint64, C.c_uint, C.c_int]
+        L.ref_bipartite_entry_points.argtypes = [C.c_uint32, C.c_uint32, _u32p]
+        L.ref_search_bipartite.restype = C.c_int
+        L.ref_search_bipartite.argtypes = [C.c_void_p, _f32p, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_uint32, _u32p,
+                                           _f32p, _u32p, _u32p, _u32p, C.POINTER(C.c_double)]
         L.ref_last_error.restype = C.c_char_p
         L.ref_num_procs.restype = C.c_int
         L.ref_distance.restype = C.c_float
@@ -196,6 +210,38 @@ class Reference:
 
     def index_free(self, h):
         self.lib.ref_index_free(h)
+
+    # -- SearchBipartiteGraph (src/index_bipartite.cpp:282-356) ----------------------------------------------------
+    def bipartite_load(self, base_fbin, bipartite_index_file, metric, padded_dim, n_sq, threads, quiet=True):
+        """tests/test_search_bipartite.cpp:158-168: ctor -> LoadSearchNeededData -> Load -> InitVisitedListPool."""
+        h = self.lib.ref_bipartite_load(base_fbin.encode(), bipartite_index_file.encode(), METRIC[metric], padded_dim,
+                                        n_sq, threads, int(quiet))
+        if not h:
+            raise RuntimeError("reference bipartite index load failed: " + self.err())
+        return h
+
+    def bipartite_entry_points(self, seed_word: int, nd: int) -> np.ndarray:
+        """The 10 ids mt19937(seed_word) + uniform_int_distribution(0, nd - 1) yield (:287-294), libstdc++'s own."""
+        out = np.zeros(10, dtype=np.uint32)
+        self.lib.ref_bipartite_entry_points(seed_word & 0xffffffff, nd, out)
+        return out
+
+    def search_bipartite(self, h, queries, k, L, threads, seed_base=0):
+        """The reference's SearchBipartiteGraph over a batch.  With the detrand library query i draws its entry points
+        from the seed word seed_base + i and `init_ids` returns them; with the plain library they are unseeded."""
+        nq = queries.shape[0]
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        dists = np.zeros((nq, k), dtype=np.float32)
+        cmps = np.zeros(nq, dtype=np.uint32)
+        hops = np.zeros(nq, dtype=np.uint32)
+        init = np.zeros((nq, 10), dtype=np.uint32)
+        wall = C.c_double(0.0)
+        rc = self.lib.ref_search_bipartite(h, queries, nq, k, L, threads, seed_base & 0xffffffff, ids, dists, cmps, hops,
+                                           init, C.byref(wall))
+        if rc != 0:
+            raise RuntimeError(self.err())
+        return dict(ids=ids, dists=dists, cmps=cmps, hops=hops, init_ids=init if self.detrand else None,
+                    wall_s=wall.value)
 
 
 def run_ref_build_roargraph(base_fbin, train_fbin, knn_file, out_index, dist, M_sq, M_pjbp, L_pjpq, threads, quiet=True,

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstring>
 #include <iostream>
+#include <random>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -199,6 +200,106 @@ int ref_search_roargraph(void *h, const float *queries, uint64_t nq, unsigned k,
         if (!err.empty()) {
             g_err = err;
             return -2;
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// ---- SearchBipartiteGraph (src/index_bipartite.cpp:282-356) ------------------------------------------------------------
+// tests/test_search_bipartite.cpp:158-168: ctor(padded dim, base_num + sq_num) -> LoadSearchNeededData -> Load ->
+// InitVisitedListPool.  `n_sq` only sizes the ctor argument (the search reads nd_ from the base file).
+void *ref_bipartite_load(const char *base_fbin, const char *bipartite_index_file, int metric, unsigned padded_dim,
+                         uint64_t n_sq, unsigned num_threads, int quiet) {
+    try {
+        Quiet q(quiet != 0);
+        uint32_t base_num, base_dim;
+        efanna2e::load_meta<float>(base_fbin, base_num, base_dim);
+        auto *r = new RefIndex();
+        r->index = new efanna2e::IndexBipartite(padded_dim, base_num + n_sq, to_metric(metric), nullptr);
+        r->index->LoadSearchNeededData(base_fbin, "");
+        r->index->Load(bipartite_index_file);
+        r->index->InitVisitedListPool(num_threads);
+        r->dim = padded_dim;
+        r->nd = base_num;
+        r->threads_inited = (int)num_threads;
+        r->own_base = true;
+        return r;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+// 1 when this library was built with oracle/shims/fixed_random_device.h pre-included (libref_roargraph_detrand.so):
+// the word std::random_device returns inside SearchBipartiteGraph is then the one set below, per query.
+int ref_has_fixed_random_device() {
+#ifdef RG_DETRAND
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+// The 10 entry points the reference derives from one random_device word (:287-294): libstdc++'s own mt19937 and
+// uniform_int_distribution, driven exactly as the reference drives them.
+void ref_bipartite_entry_points(uint32_t seed_word, uint32_t nd, uint32_t *out10) {
+    std::mt19937 gen(seed_word);
+    std::uniform_int_distribution<uint32_t> dis(0, nd - 1);
+    for (uint32_t i = 0; i < 10; ++i) out10[i] = dis(gen);
+}
+
+// The timed loop of tests/test_search_bipartite.cpp:196-209 for one L_pq.  With the fixed random_device, query i sees the
+// seed word seed_base + i (whatever thread runs it) and init_ids_out[i*10..] receives the entry points that word yields;
+// without it the entry points are the reference's own unseeded draw and init_ids_out is left untouched.
+int ref_search_bipartite(void *h, const float *queries, uint64_t nq, unsigned k, unsigned L_pq, unsigned num_threads,
+                         uint32_t seed_base, unsigned *ids, float *dists, unsigned *cmps, unsigned *hops,
+                         uint32_t *init_ids_out, double *wall_s) {
+    RefIndex *r = (RefIndex *)h;
+    try {
+        efanna2e::Parameters parameters;
+        parameters.Set<uint32_t>("num_threads", num_threads);
+        parameters.Set<uint32_t>("L_pq", L_pq);
+        omp_set_num_threads(num_threads);
+        const size_t dim = r->dim;
+        std::string err;
+        int bad_draws = 0;
+        auto start = std::chrono::high_resolution_clock::now();
+#pragma omp parallel for schedule(dynamic, 1)
+        for (size_t i = 0; i < nq; ++i) {
+            std::vector<float> d(k, 0.0f);
+            try {
+#ifdef RG_DETRAND
+                rg_detrand::next_seed = seed_base + (uint32_t)i;
+                const uint64_t before = rg_detrand::calls;
+                if (init_ids_out) ref_bipartite_entry_points(seed_base + (uint32_t)i, r->nd, init_ids_out + i * 10);
+#endif
+                auto ret = r->index->SearchBipartiteGraph(queries + i * dim, k, i, parameters, ids + i * k, d);
+#ifdef RG_DETRAND
+                if (rg_detrand::calls != before + 1) {
+#pragma omp atomic
+                    bad_draws++;
+                }
+#endif
+                if (cmps) cmps[i] = ret.first;
+                if (hops) hops[i] = ret.second;
+                if (dists) std::memcpy(dists + i * k, d.data(), k * sizeof(float));
+            } catch (const std::exception &e) {
+#pragma omp critical
+                err = e.what();
+            }
+        }
+        auto end = std::chrono::high_resolution_clock::now();
+        if (wall_s) *wall_s = std::chrono::duration<double>(end - start).count();
+        if (!err.empty()) {
+            g_err = err;
+            return -2;
+        }
+        if (bad_draws) {
+            g_err = "SearchBipartiteGraph did not draw exactly one random_device word per query";
+            return -3;
         }
         return 0;
     } catch (const std::exception &e) {

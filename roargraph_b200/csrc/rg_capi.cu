@@ -244,8 +244,12 @@ int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_
         for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
             const uint32_t v = nbrs[j];
             if (v >= n_total) { set_error("rg_index_set_bipartite: neighbour id out of range"); return RG_EINVAL; }
-            // query nodes (u >= nd) must point at base nodes: they are evaluated against the base array (:334)
+            // The graph is bipartite (qbaseNNbipartite, :262-273): a query node (u >= nd) points at base nodes, which the
+            // search evaluates against the base array and tags in a visited array of nd entries (:326-334); a base node
+            // points at query nodes, whose lists are walked as second hops.  A base -> base edge would make a base id a
+            // "query node" and its neighbours' neighbours — possibly query-node ids >= nd — rows of the base array.
             if (u >= idx->nd && v >= idx->nd) { set_error("rg_index_set_bipartite: query node points at a query node"); return RG_EINVAL; }
+            if (u < idx->nd && v < idx->nd) { set_error("rg_index_set_bipartite: base node points at a base node"); return RG_EINVAL; }
             if (std::find(out.begin() + start, out.end(), v) == out.end()) out.push_back(v);
         }
         ro[u + 1] = out.size();

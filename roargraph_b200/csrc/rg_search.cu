@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
             for (uint32_t i = lane; i < p.k; i += 32) {
                 const bool ok = i < w.size;
                 p.out_ids[(size_t)qidx * p.k + i] = ok ? (w.qi[i] & kIdMask) : 0xffffffffu;
-                p.out_dists[(size_t)qidx * p.k + i] = ok ? w.qd[i] : 0.f;
+                p.out_dists[(size_t)qidx * p.k + i] = ok ? w.qd[i] : INFINITY;  // missing slots sort last in any merge
             }
         }
         if (lane == 0) {

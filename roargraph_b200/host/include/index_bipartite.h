@@ -72,8 +72,12 @@ class IndexBipartite : public Index {
   // queries: nq x GetDimension(); indices/dists: nq x k; cmps/hops: nq (may be null)
   void SearchRoarGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters, unsigned *indices,
                             float *dists, uint32_t *cmps, uint32_t *hops);
-  // init_ids: nq x n_init entry points, or null to draw them from `seed` (the reference draws 10 per query from an
-  // unseeded std::random_device, src/index_bipartite.cpp:287-294)
+  // init_ids: nq x n_init entry points, or null to draw them on the host the way the reference does
+  // (src/index_bipartite.cpp:287-294: one std::random_device word per query -> std::mt19937 ->
+  // std::uniform_int_distribution<uint32_t>(0, nd - 1)); query i's word is (uint32_t)(seed + i), or an unseeded
+  // std::random_device word when seed == kRandomDeviceSeed
+  static constexpr uint64_t kRandomDeviceSeed = ~0ull;
+  void DrawEntryPoints(size_t nq, uint32_t n_init, uint64_t seed, std::vector<uint32_t> &out) const;
   void SearchBipartiteGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
                                  const uint32_t *init_ids, uint32_t n_init, uint64_t seed, unsigned *indices, float *dists,
                                  uint32_t *cmps, uint32_t *hops);

@@ -9,6 +9,7 @@
 #include <fstream>
 #include <iostream>
 #include <mutex>
+#include <random>
 #include <stdexcept>
 
 #include "rg_b200.h"
@@ -350,6 +351,27 @@ std::pair<uint32_t, uint32_t> IndexBipartite::SearchRoarGraph(const float *query
   return {cmps, hops};
 }
 
+// Entry points the way the reference draws them (src/index_bipartite.cpp:287-294): ONE std::random_device word per query
+// seeds a std::mt19937 whose first n_init draws through std::uniform_int_distribution<uint32_t>(0, nd - 1) are the ids.
+// seed_word(i) = the word query i uses: an unseeded std::random_device like the reference, or (uint32_t)(seed + i) so
+// that a run is reproducible — and comparable id for id with the reference compiled against a fixed random_device.
+void IndexBipartite::DrawEntryPoints(size_t nq, uint32_t n_init, uint64_t seed, std::vector<uint32_t> &out) const {
+  out.resize(nq * n_init);
+  const uint32_t u32_nd = (uint32_t)nd_;
+  for (size_t i = 0; i < nq; ++i) {
+    uint32_t word;
+    if (seed == kRandomDeviceSeed) {
+      std::random_device rd;
+      word = rd();
+    } else {
+      word = (uint32_t)(seed + i);
+    }
+    std::mt19937 gen(word);
+    std::uniform_int_distribution<uint32_t> dis(0, u32_nd - 1);
+    for (uint32_t j = 0; j < n_init; ++j) out[i * n_init + j] = dis(gen);
+  }
+}
+
 void IndexBipartite::SearchBipartiteGraphBatch(const float *queries, size_t nq, size_t k, const Parameters &parameters,
                                                const uint32_t *init_ids, uint32_t n_init, uint64_t seed,
                                                unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
@@ -357,16 +379,23 @@ void IndexBipartite::SearchBipartiteGraphBatch(const float *queries, size_t nq, 
   std::lock_guard<std::mutex> guard(call_mutex_);
   if (!bipartite_uploaded_ && !bipartite_graph_.empty() && data_bp_) UploadBipartiteGraph();
   if (!dev_) throw std::runtime_error("index not loaded");
-  int rc = rg_search_bipartite(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, init_ids, n_init, seed, indices, dists, cmps, hops);
+  std::vector<uint32_t> drawn;
+  if (!init_ids) {
+    DrawEntryPoints(nq, n_init, seed, drawn);
+    init_ids = drawn.data();
+  }
+  int rc = rg_search_bipartite(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, init_ids, n_init, 0, indices, dists, cmps, hops);
   if (rc != RG_OK) Fail(rc);
 }
 
 std::pair<uint32_t, uint32_t> IndexBipartite::SearchBipartiteGraph(const float *query, size_t k, size_t &qid,
                                                                    const Parameters &parameters, unsigned *indices,
                                                                    std::vector<float> &dists) {
+  (void)qid;  // unused by the reference as well
   uint32_t cmps = 0, hops = 0;
   dists.resize(k);
-  SearchBipartiteGraphBatch(query, 1, k, parameters, nullptr, 10, (uint64_t)qid, indices, dists.data(), &cmps, &hops);
+  // the drop-in single-query entry draws from std::random_device exactly like the reference (:287-294)
+  SearchBipartiteGraphBatch(query, 1, k, parameters, nullptr, 10, kRandomDeviceSeed, indices, dists.data(), &cmps, &hops);
   return {cmps, hops};
 }
 

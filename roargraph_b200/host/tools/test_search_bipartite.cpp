@@ -3,8 +3,9 @@
 // (L_pq,qps,avg_cmps,ms_per_query,recall,rderr,avg_hops), one batched device call per L_pq where the reference loops
 // `#pragma omp parallel for` over SearchBipartiteGraph (:203-208).
 // The reference draws 10 random base entry points per query from an unseeded std::random_device
-// (src/index_bipartite.cpp:287-294), so its table differs run to run; here they are drawn from --seed (default 0) and
-// the table is reproducible.  --seed is the one added flag.
+// (src/index_bipartite.cpp:287-294: one random_device word per query -> mt19937 -> uniform_int_distribution), so its table
+// differs run to run; here query i's word is --seed + i (default seed 0; "--seed random" = unseeded like the reference)
+// and the ids are derived from the word exactly as the reference derives them.  --seed is the one added flag.
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -60,7 +61,7 @@ int main(int argc, char **argv) {
       .add("L_pq", "Priority queue length for searching", true, true).numeric()
       .add("k", "k nearest neighbors", true, false, "1").numeric()
       .add("evaluation_save_path", "Path prefix for saving evaluation results", false)
-      .add("seed", "seed of the 10 random entry points per query (the reference's are unseeded)", false, false, "0").numeric()
+      .add("seed", "query i draws its 10 entry points from the random_device word seed + i; 'random' = unseeded like the reference", false, false, "0")
       .add("num_threads", "Number of host threads (kept for compatibility; the search runs on the GPU)", false, false,
            std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T').numeric();
   try {
@@ -75,7 +76,17 @@ int main(int argc, char **argv) {
                     eval_path = args.str("evaluation_save_path");
   const std::vector<uint32_t> L_vec = args.u32_list("L_pq");
   const uint32_t k = (uint32_t)args.u64("k"), num_threads = (uint32_t)args.u64("num_threads");
-  const uint64_t seed = args.u64("seed");
+  uint64_t seed = efanna2e::IndexBipartite::kRandomDeviceSeed;
+  if (args.str("seed") != "random") {
+    try {
+      size_t pos = 0;
+      seed = std::stoull(args.str("seed"), &pos);
+      if (pos != args.str("seed").size()) throw std::invalid_argument("seed");
+    } catch (const std::exception &) {
+      std::cerr << "the argument ('" << args.str("seed") << "') for option '--seed' is invalid" << '\n';
+      return -1;
+    }
+  }
 
   try {
     uint32_t base_num, base_dim, sq_num, sq_dim;

@@ -30,6 +30,25 @@ def index_words_to_csr(words):
     return ep, row_off, (np.concatenate(nbrs).astype(np.uint32) if nbrs else np.zeros(0, np.uint32))
 
 
+def bipartite_words_to_csr(words):
+    """Decode the raw bipartite-index file words (u32 npts, {deg, ids}*; src/index_bipartite.cpp:2045-2071)."""
+    fake = np.concatenate([np.zeros(1, np.uint32), words])  # same stream as a projection index behind an entry-point word
+    _, row_off, nbrs = index_words_to_csr(fake)
+    return row_off, nbrs
+
+
+class BipartiteGolden:
+    """tests/golden/bipartite_<name>.npz: outputs of the reference's SearchBipartiteGraph compiled with a fixed
+    std::random_device word per query (make_golden.py bipartite)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, f"bipartite_{name}.npz"))
+        self.z = z
+        self.k = int(z["k"])
+        self.cases = [(int(L), int(s)) for L, s in z["cases"]]
+        self.row_off, self.nbrs = bipartite_words_to_csr(z["graph_words"])
+
+
 class GoldenCase:
     def __init__(self, name):
         from roargraph_b200 import formats as F

@@ -6,7 +6,7 @@ import pytest
 
 import roargraph_b200 as rg
 from gpu_helpers import assert_same_search, bipartite_from_knn, bits, build_reference_case, random_graph
-from oracle.oracle import have_reference
+from oracle.oracle import have_detrand_reference, have_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -188,6 +188,82 @@ def test_bipartite_parity(oracle, golden):
     a = idx.search_bipartite(queries, 3, 50, seed=42)
     b = idx.search_bipartite(queries, 3, 50, seed=42)
     assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
+    idx.close()
+
+
+def test_bipartite_golden_parity(oracle, golden):
+    """Committed outputs of the compiled reference's SearchBipartiteGraph (tests/golden/bipartite_*.npz)."""
+    from conftest import BipartiteGolden
+    b = BipartiteGolden(golden.name)
+    base, queries = golden.normalised(oracle)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_bipartite(b.row_off, b.nbrs)
+    for L, _ in b.cases:
+        want = {k: b.z[f"{k}_L{L}"] for k in ("ids", "dists", "cmps", "hops")}
+        assert_same_search(idx.search_bipartite(queries, b.k, L, init_ids=b.z[f"init_ids_L{L}"]), want, f"{golden.name} L={L}")
+    idx.close()
+
+
+@pytest.mark.skipif(not have_detrand_reference(), reason="oracle/_ref/libref_roargraph_detrand.so not available")
+def test_bipartite_parity_vs_compiled_reference(golden, oracle, tmp_path):
+    """A2 pinned by execution: the reference's own SearchBipartiteGraph (compiled with a fixed std::random_device word per
+    query, oracle/shims/fixed_random_device.h) and the GPU kernel given the entry points that word yields: ids, distance
+    bits, cmps, hops."""
+    from oracle.oracle import Reference
+    from roargraph_b200 import formats as F
+    R = Reference(detrand=True)
+    base, queries = golden.normalised(oracle)
+    nd = base.shape[0]
+    row_off, nbrs = bipartite_from_knn(golden.z["train_knn_ids"], nd, 16)
+    bf, gf = str(tmp_path / "base.fbin"), str(tmp_path / "bp.rg")
+    F.write_fbin(bf, golden.base_raw)
+    F.write_bipartite_index(gf, row_off, nbrs)
+    h = R.bipartite_load(bf, gf, golden.metric, base.shape[1], golden.z["train_knn_ids"].shape[0], 2)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_bipartite(row_off, nbrs)
+    checked = 0
+    for L, seed in ((10, 1), (50, 2), (300, 3), (2000, 4)):
+        try:
+            want = R.search_bipartite(h, queries, golden.k, L, 2, seed_base=seed)
+        except RuntimeError as e:  # some query's entry points reach fewer than k nodes: both sides must fail alike
+            assert "not enough results" in str(e)
+            init = np.stack([R.bipartite_entry_points(seed + i, nd) for i in range(queries.shape[0])])
+            with pytest.raises(rg.RgError) as ge:
+                idx.search_bipartite(queries, golden.k, L, init_ids=init)
+            assert ge.value.code == rg.RG_ENOTENOUGH
+            continue
+        assert_same_search(idx.search_bipartite(queries, golden.k, L, init_ids=want["init_ids"]), want,
+                           f"bipartite vs compiled reference L={L}")
+        checked += 1
+    assert checked >= 2
+    R.index_free(h)
+    idx.close()
+
+
+@pytest.mark.skipif(not have_detrand_reference(), reason="oracle/_ref/libref_roargraph_detrand.so not available")
+@pytest.mark.parametrize("nb,dim,metric", [(60000, 200, "ip"), (30000, 96, "l2")])
+def test_bipartite_live_reference_parity_at_scale(nb, dim, metric, tmp_path):
+    """The same pin on a graph of README shape (M_pjbp = 35, as many training queries as base rows so that most base
+    nodes own a query node): 500 queries over the sweep's range, every id / distance bit / cmps / hops."""
+    from oracle.oracle import Reference
+    from roargraph_b200 import formats as F, synth
+    R = Reference(detrand=True)
+    base, train, test = synth.make_numpy(nb, nb, 500, dim, seed=77)
+    knn, _ = rg.knn(base, train, 35, metric)
+    row_off, nbrs = bipartite_from_knn(knn.astype(np.uint32), nb, 35)
+    bf, gf = str(tmp_path / "base.fbin"), str(tmp_path / "bp.rg")
+    F.write_fbin(bf, base)
+    F.write_bipartite_index(gf, row_off, nbrs)
+    threads = R.num_procs()
+    h = R.bipartite_load(bf, gf, metric, F.pad_rows(base).shape[1], nb, threads)
+    b = R.index_base(h, nb, F.pad_rows(base).shape[1]).copy()
+    q = F.pad_rows(test)
+    idx = rg.RoarIndex(b, metric)
+    idx.set_bipartite(row_off, nbrs)
+    for L in (10, 50, 200, 1000):
+        want = R.search_bipartite(h, q, 10, L, threads, seed_base=1000 * L)
+        assert_same_search(idx.search_bipartite(q, 10, L, init_ids=want["init_ids"]), want, f"{metric} nb={nb} L={L}")
+    R.index_free(h)
     idx.close()
 
 

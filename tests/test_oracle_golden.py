@@ -72,3 +72,21 @@ def test_normalised_rows_of_the_cosine_fixture(oracle):
     g = GoldenCase("cos_d64")
     assert (oracle.normalize_rows(g.base.copy()).view(np.uint32) == g.z["base_norm"].view(np.uint32)).all()
     assert (oracle.normalize_rows(g.queries.copy()).view(np.uint32) == g.z["queries_norm"].view(np.uint32)).all()
+
+
+def test_search_bipartite_matches_reference(oracle, golden):
+    """A2 against committed outputs of the compiled reference (fixed std::random_device word per query): given the stored
+    entry points the restatement returns the stored ids, distance bits, cmps and hops."""
+    from conftest import BipartiteGolden
+    from gpu_helpers import bipartite_from_knn
+    b = BipartiteGolden(golden.name)
+    base, queries = golden.normalised(oracle)
+    # the file the reference's build CLI wrote at -T 1 is what qbaseNNbipartite's definition gives (:235-280)
+    want_off, want_nbrs = bipartite_from_knn(golden.z["train_knn_ids"], base.shape[0], int(b.z["M_pjbp"]))
+    assert (b.row_off == want_off).all() and (b.nbrs == want_nbrs).all()
+    for L, _ in b.cases:
+        r = oracle.search_bipartite(base, b.row_off, b.nbrs, b.z[f"init_ids_L{L}"], golden.metric, queries, b.k, L, 2)
+        assert r["nfail"] == 0
+        assert (r["ids"] == b.z[f"ids_L{L}"]).all()
+        assert (bits(r["dists"]) == bits(b.z[f"dists_L{L}"])).all()
+        assert (r["cmps"] == b.z[f"cmps_L{L}"]).all() and (r["hops"] == b.z[f"hops_L{L}"]).all()
