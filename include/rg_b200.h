@@ -40,11 +40,14 @@ extern "C" {
 #define RG_ENOMEM (-5)
 
 typedef struct rg_index rg_index;
+typedef struct rg_knn_base rg_knn_base;
 
 const char *rg_last_error(void);
 /* ABI version of this header. */
 int rg_abi_version(void);
-/* Select the CUDA device this process drives (one process per GPU).  Optional; default device 0. */
+/* Make `device` the calling thread's current CUDA device (one process — or one host thread — per GPU).  Optional: without
+ * it the library adopts whatever device is current on the calling thread (device 0 in a fresh thread).  An rg_index /
+ * rg_knn_base remembers the device it was created on and switches to it on every call. */
 int rg_init(int device);
 /* Number of SMs etc. of the active device; returns <0 when no device is usable. */
 int rg_device_sm_count(void);
@@ -126,6 +129,22 @@ int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, ui
            int32_t id_offset, int32_t *ids, float *dists);
 int rg_knn_dev(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
                int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, void *stream);
+
+/* The base side of exact_knn prepared ONCE for any number of query batches — compute_groundtruth keeps a base part in
+ * memory and walks the queries past it 1 024 at a time (compute_groundtruth.cpp:187-200, part loop :396-416): squared norms,
+ * the normalised copy for COSINE, the bf16 operand copy.  base_on_device != 0: `base` is a device pointer that outlives the
+ * object (no copy); otherwise host rows copied to HBM once.  rg_knn_base_search_dev scores one batch of device-resident
+ * queries against it; results as rg_knn_dev.  Used by the base-sharded 10 M x 10 M run (BASELINE configs[3]): every GPU
+ * keeps its shard prepared while the query batches stream past. */
+int rg_knn_base_create(rg_knn_base **out, const float *base, uint64_t nb, uint32_t dim, int metric, int base_on_device);
+int rg_knn_base_destroy(rg_knn_base *kb);
+int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
+                           int32_t *d_ids, float *d_dists, void *stream);
+/* Device milliseconds per phase of this thread's kNN calls since the last rg_knn_profile_reset(), measured only when the
+ * environment has RG_KNN_TRACE=1 (events + a synchronisation per phase: a diagnostic pass, never the timed one).
+ * out[0..6] = base preparation, query conversion, tau seed pass, tensor-core filter, re-rank/merge, chunks, overflow retries. */
+int rg_knn_profile(double *out7);
+int rg_knn_profile_reset(void);
 
 /* rg_knn / rg_knn_dev keep their device scratch (bf16 operand copies, candidate lists; a few GB at 10 M rows) in a
  * grow-only per-process workspace so that repeated calls do not pay cudaMalloc/cudaFree; this gives it back. */

@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
         L.rg_knn.argtypes = [vp, u64, vp, u64, u32, u32, C.c_int, i32, vp, vp]
         L.rg_knn_dev.argtypes = [vp, u64, vp, u64, u32, u32, C.c_int, i32, vp, vp, vp]
         L.rg_topk_merge_dev.argtypes = [vp, vp, u32, u64, u32, vp, vp, vp]
+        L.rg_knn_base_create.argtypes = [C.POINTER(vp), vp, u64, u32, C.c_int, C.c_int]
+        L.rg_knn_base_destroy.argtypes = [vp]
+        L.rg_knn_base_search_dev.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp]
+        L.rg_knn_profile.argtypes = [C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -261,6 +265,54 @@ def knn_dev(d_base, d_queries, K: int, metric: str | int, d_ids, d_dists, id_off
     _check(lib().rg_knn_dev(C.c_void_p(d_base.data_ptr()), d_base.shape[0], C.c_void_p(d_queries.data_ptr()),
                             d_queries.shape[0], d_base.shape[1], K, m, id_offset, C.c_void_p(d_ids.data_ptr()),
                             C.c_void_p(d_dists.data_ptr()), _stream_ptr(stream)))
+
+
+class KnnBase:
+    """The base side of exact_knn prepared once (norms, normalised copy for cosine, bf16 operand copy) for any number of
+    query batches — compute_groundtruth's base part kept in memory while the queries walk past it
+    (compute_groundtruth.cpp:187-200, :396-416).  `base`: float32 numpy matrix (copied to HBM) or CUDA torch tensor (used in
+    place; must outlive the object)."""
+
+    def __init__(self, base, metric: str | int):
+        self._h = C.c_void_p(0)
+        m = METRIC[metric] if isinstance(metric, str) else int(metric)
+        if isinstance(base, np.ndarray):
+            b = np.ascontiguousarray(base, dtype=np.float32)
+            self._keep = None
+            self.nb, self.dim = b.shape
+            _check(lib().rg_knn_base_create(C.byref(self._h), _np_ptr(b), self.nb, self.dim, m, 0))
+        else:
+            if not base.is_cuda or not base.is_contiguous() or base.dim() != 2 or str(base.dtype) != "torch.float32":
+                raise RgError(RG_EINVAL, "base must be a contiguous float32 CUDA tensor")
+            self._keep = base
+            self.nb, self.dim = base.shape
+            _check(lib().rg_knn_base_create(C.byref(self._h), C.c_void_p(base.data_ptr()), self.nb, self.dim, m, 1))
+
+    def search_dev(self, d_queries, K: int, d_ids, d_dists, id_offset: int = 0, stream=None) -> None:
+        _check(lib().rg_knn_base_search_dev(self._h, C.c_void_p(d_queries.data_ptr()), d_queries.shape[0], K, id_offset,
+                                            C.c_void_p(d_ids.data_ptr()), C.c_void_p(d_dists.data_ptr()),
+                                            _stream_ptr(stream)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rg_knn_base_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def knn_profile(reset: bool = False) -> dict:
+    """Device ms per phase of this thread's kNN calls (only filled under RG_KNN_TRACE=1)."""
+    out = (C.c_double * 7)()
+    _check(lib().rg_knn_profile(out))
+    if reset:
+        lib().rg_knn_profile_reset()
+    keys = ("convert_base_ms", "convert_queries_ms", "seed_ms", "filter_ms", "merge_ms", "chunks", "overflow_retries")
+    return {k: float(v) for k, v in zip(keys, out)}
 
 
 def knn_release_workspace() -> None:

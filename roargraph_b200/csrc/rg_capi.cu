@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,11 +21,15 @@ int cuda_fail(cudaError_t e, const char *what) {
     return RG_ECUDA;
 }
 
-static int g_device = 0;
-static int g_sm_count = -1;
+// Device bookkeeping.  The library never picks a device on its own: every entry point works on the calling thread's
+// current CUDA device (rg_init just makes one current), and index / kNN-base objects remember theirs — so several host
+// threads can each drive their own GPU of one process (include/rg_b200.h, rg_group_*).
+constexpr int kMaxDev = 64;
+static std::mutex g_dev_mu;
+static int g_dev_sms[kMaxDev] = {};   // 0 = not probed yet, -1 = unusable
+static bool g_l2_fetch_done[kMaxDev] = {};
 
 static int ensure_device() {
-    if (g_sm_count > 0) return RG_OK;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -32,20 +37,28 @@ static int ensure_device() {
         set_error("no CUDA device available (librg_b200 has no CPU fallback)");
         return RG_ECUDA;
     }
-    RG_CUDA(cudaSetDevice(g_device));
+    int dev = 0;
+    RG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) { set_error("CUDA device index out of range"); return RG_ECUDA; }
+    std::lock_guard<std::mutex> g(g_dev_mu);
+    if (g_dev_sms[dev] > 0) return RG_OK;
     cudaDeviceProp prop;
-    RG_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    RG_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) {
+        g_dev_sms[dev] = -1;
         set_error("librg_b200 is built for sm_100a (B200) only");
         return RG_ECUDA;
     }
-    g_sm_count = prop.multiProcessorCount;
+    g_dev_sms[dev] = prop.multiProcessorCount;
     // The beam search gathers 800-byte / 2 KB rows at random: RG_L2_FETCH=32|64|128 sets the granularity at which L2
     // fetches from HBM (a hint; the driver's default over-fetches around short rows)
-    if (const char *v = getenv("RG_L2_FETCH")) {
-        const size_t g = (size_t)strtoul(v, nullptr, 10);
-        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
-        cudaGetLastError();
+    if (!g_l2_fetch_done[dev]) {
+        g_l2_fetch_done[dev] = true;
+        if (const char *v = getenv("RG_L2_FETCH")) {
+            const size_t gr = (size_t)strtoul(v, nullptr, 10);
+            if (gr == 32 || gr == 64 || gr == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gr);
+            cudaGetLastError();
+        }
     }
     return RG_OK;
 }
@@ -55,8 +68,20 @@ static int ensure_device() {
 using namespace rg;
 
 namespace rg {
-int sm_count() { return g_sm_count; }
+int sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 0;
+    std::lock_guard<std::mutex> g(g_dev_mu);
+    return g_dev_sms[dev] > 0 ? g_dev_sms[dev] : 0;
+}
 int ensure_device_ready() { return ensure_device(); }
+int enter_index(rg_index *idx) {
+    if (!idx) { set_error("null index"); return RG_EINVAL; }
+    int dev = 0;
+    RG_CUDA(cudaGetDevice(&dev));
+    if (dev != idx->device) RG_CUDA(cudaSetDevice(idx->device));
+    return RG_OK;
+}
 }
 
 int rg::ensure_tags(rg_index *idx, uint32_t slots) {
@@ -100,7 +125,7 @@ uint32_t rg::affordable_slots(rg_index *idx) {
     size_t budget = (free_b + (size_t)idx->n_slots * idx->tag_stride) / 3;  // at most a third of what is free
     size_t s = budget / idx->tag_stride;
     if (s < 4) s = 4;
-    if (s > max_search_slots(g_sm_count)) s = max_search_slots(g_sm_count);
+    if (s > max_search_slots(idx->sm_count)) s = max_search_slots(idx->sm_count);
     return (uint32_t)s;
 }
 
@@ -142,14 +167,20 @@ const char *rg_last_error(void) { return g_err.c_str(); }
 int rg_abi_version(void) { return 1; }
 
 int rg_init(int device) {
-    g_device = device;
-    g_sm_count = -1;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (librg_b200 has no CPU fallback)");
+        return RG_ECUDA;
+    }
+    if (device < 0 || device >= n) { set_error("rg_init: no such CUDA device"); return RG_EINVAL; }
+    RG_CUDA(cudaSetDevice(device));
     return ensure_device();
 }
 
 int rg_device_sm_count(void) {
     int rc = ensure_device();
-    return rc == RG_OK ? g_sm_count : rc;
+    return rc == RG_OK ? sm_count() : rc;
 }
 
 int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim, int metric, int base_on_device) {
@@ -163,6 +194,8 @@ int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim
     int rc = ensure_device();
     if (rc != RG_OK) return rc;
     rg_index *idx = new rg_index();
+    cudaGetDevice(&idx->device);
+    idx->sm_count = sm_count();
     idx->nd = nd;
     idx->dim = dim;
     idx->metric = metric;
@@ -196,6 +229,7 @@ int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim
 int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, const uint32_t *nbrs) {
     if (!idx || !row_off || (!nbrs && row_off[idx->nd] != 0)) { set_error("rg_index_set_graph: null argument"); return RG_EINVAL; }
     if (ep >= idx->nd) { set_error("rg_index_set_graph: entry point out of range"); return RG_EINVAL; }
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     const uint64_t nd = idx->nd;
     // Pass 1: duplicate-free degree of every row.  The reference's visited array makes a repeated id inside one
     // adjacency list a no-op (src/index_bipartite.cpp:2378), so dropping repeats at upload changes nothing observable.
@@ -235,6 +269,7 @@ int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, cons
 
 int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_off, const uint32_t *nbrs) {
     if (!idx || !row_off || n_total < idx->nd) { set_error("rg_index_set_bipartite: bad argument"); return RG_EINVAL; }
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     // dedupe each list (same argument as in rg_index_set_graph) while rebuilding the CSR
     std::vector<uint64_t> ro(n_total + 1, 0);
     std::vector<uint32_t> out;
@@ -269,6 +304,7 @@ int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_
 
 int rg_index_destroy(rg_index *idx) {
     if (!idx) return RG_OK;
+    enter_index(idx);
     if (idx->own_base && idx->d_base) cudaFree((void *)idx->d_base);
     if (idx->d_adj) cudaFree(idx->d_adj);
     if (idx->d_row_off) cudaFree(idx->d_row_off);
@@ -292,6 +328,7 @@ int rg_index_destroy(rg_index *idx) {
 int rg_index_build_roargraph(rg_index *idx, const uint32_t *knn_ids, int knn_on_device, uint64_t nsq,
                              uint32_t knn_stride, uint32_t M_sq, uint32_t M_pjbp, uint32_t L_pjpq, uint32_t n_rounds) {
     if (!idx || !knn_ids || nsq == 0 || knn_stride == 0) { set_error("rg_index_build_roargraph: null/empty argument"); return RG_EINVAL; }
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     const uint32_t *d_knn = knn_ids;
     uint32_t *tmp = nullptr;
     if (!knn_on_device) {
@@ -309,6 +346,7 @@ int rg_index_graph_size(rg_index *idx, uint64_t *nnz, uint32_t *ep, uint32_t *ma
     if (!idx) { set_error("null index"); return RG_EINVAL; }
     if (!idx->has_graph) { set_error("projection graph not set"); return RG_ESTATE; }
     uint64_t total = 0;
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     int rc = adjacency_nnz_device(idx->d_adj, idx->adj_stride, idx->nd, &total);
     if (rc != RG_OK) return rc;
     if (nnz) *nnz = total;
@@ -321,6 +359,7 @@ int rg_index_get_graph(rg_index *idx, uint64_t *row_off, uint32_t *nbrs) {
     if (!idx || !row_off) { set_error("rg_index_get_graph: null argument"); return RG_EINVAL; }
     if (!idx->has_graph) { set_error("projection graph not set"); return RG_ESTATE; }
     const uint64_t nd = idx->nd;
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     const uint32_t stride = idx->adj_stride;
     // stream the fixed-stride rows back in slabs and compact them into CSR
     const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / (stride * 4ull));
@@ -345,6 +384,7 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
     SearchParams p;
     int rc = fill_params(idx, p, nq, k, L);
     if (rc != RG_OK) return rc;
+    if ((rc = enter_index(idx)) != RG_OK) return rc;
     if (nq == 0) return RG_OK;
     if (!d_q || !d_ids || !d_dists) { set_error("search: null buffer"); return RG_EINVAL; }
     if (bipartite) {
@@ -401,12 +441,12 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
     }
     // cudaMemGetInfo (affordable_slots) costs milliseconds and serialises with the device: only ask when this launch wants
     // more slots than already have tag arrays
-    rc = plan_search(p, l, g_sm_count, 0xffffffffu);
+    rc = plan_search(p, l, idx->sm_count, 0xffffffffu);
     if (rc != RG_OK) return rc;
     if (l.grid * l.warps_per_cta > idx->n_slots) {
         const uint32_t cap = std::max(idx->n_slots, affordable_slots(idx));
         if (l.grid * l.warps_per_cta > cap) {
-            rc = plan_search(p, l, g_sm_count, cap);
+            rc = plan_search(p, l, idx->sm_count, cap);
             if (rc != RG_OK) return rc;
         }
     }
@@ -469,6 +509,7 @@ int rg_search_bipartite_dev(rg_index *idx, const float *d_queries, uint32_t nq, 
 
 int rg_index_check(rg_index *idx, void *stream) {
     if (!idx) { set_error("null index"); return RG_EINVAL; }
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     RG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return check_latched(idx);
 }
@@ -480,6 +521,7 @@ static int search_host(rg_index *idx, bool bipartite, const float *q, uint32_t n
     if (nq == 0) return RG_OK;
     if (!q || !ids || !dists) { set_error("search: null buffer"); return RG_EINVAL; }
     int rc;
+    if ((rc = enter_index(idx)) != RG_OK) return rc;
     if ((rc = idx->q.reserve((size_t)nq * idx->dim)) != RG_OK) return rc;
     if ((rc = idx->ids.reserve((size_t)nq * k)) != RG_OK) return rc;
     if ((rc = idx->dists.reserve((size_t)nq * k)) != RG_OK) return rc;
@@ -534,6 +576,7 @@ int rg_search_bipartite(rg_index *idx, const float *queries, uint32_t nq, uint32
 
 int rg_search_last_stats(rg_index *idx, uint64_t *total_cmps, uint64_t *total_hops, uint64_t *adj_words) {
     if (!idx) { set_error("null index"); return RG_EINVAL; }
+    { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
     RG_CUDA(cudaDeviceSynchronize());
     unsigned long long st[4];
     RG_CUDA(cudaMemcpy(st, idx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
@@ -594,6 +637,57 @@ int rg_knn(const float *base, uint64_t nb, const float *queries, uint64_t nq, ui
     if (d_i) cudaFree(d_i);
     if (e != cudaSuccess) return cuda_fail(e, "rg_knn");
     return rc;
+}
+
+int rg_knn_base_create(rg_knn_base **out, const float *base, uint64_t nb, uint32_t dim, int metric, int base_on_device) {
+    if (!out || !base || nb == 0 || dim == 0) { set_error("rg_knn_base_create: null/empty argument"); return RG_EINVAL; }
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    const float *d_base = base;
+    float *own = nullptr;
+    if (!base_on_device) {
+        cudaError_t e = cudaMalloc(&own, nb * dim * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(own, base, nb * dim * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (own) cudaFree(own);
+            return cuda_fail(e, "rg_knn_base_create: base upload");
+        }
+        d_base = own;
+    }
+    rg_knn_base *kb = nullptr;
+    rc = knn_base_new(&kb, d_base, own, nb, dim, metric);
+    if (rc != RG_OK) return rc;
+    *out = kb;
+    return RG_OK;
+}
+
+int rg_knn_base_destroy(rg_knn_base *kb) {
+    knn_base_free(kb);
+    return RG_OK;
+}
+
+int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
+                           int32_t *d_ids, float *d_dists, void *stream) {
+    if (!kb) { set_error("rg_knn_base_search_dev: null base"); return RG_EINVAL; }
+    return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream);
+}
+
+int rg_knn_profile(double *out7) {
+    if (!out7) { set_error("rg_knn_profile: null buffer"); return RG_EINVAL; }
+    const KnnProfile &p = knn_last_profile();
+    out7[0] = p.convert_base_ms;
+    out7[1] = p.convert_queries_ms;
+    out7[2] = p.seed_ms;
+    out7[3] = p.filter_ms;
+    out7[4] = p.merge_ms;
+    out7[5] = (double)p.chunks;
+    out7[6] = (double)p.overflow_retries;
+    return RG_OK;
+}
+
+int rg_knn_profile_reset(void) {
+    knn_reset_profile();
+    return RG_OK;
 }
 
 int rg_knn_release_workspace(void) {

@@ -93,6 +93,8 @@ struct DevBuf {  // grow-only device scratch
 }  // namespace rg
 
 struct rg_index {
+    int device = 0;      // the CUDA device the index lives on (the current device when it was created)
+    int sm_count = 0;
     uint64_t nd = 0;
     uint32_t dim = 0;
     int metric = 0;
@@ -126,8 +128,9 @@ struct rg_index {
 
 namespace rg {
 
-int sm_count();
-int ensure_device_ready();
+int sm_count();             // SM count of the calling thread's current device (0 when there is none)
+int ensure_device_ready();  // RG_OK when the current device is a usable sm_100 GPU
+int enter_index(rg_index *idx);  // makes the index's device current on the calling thread
 int ensure_tags(rg_index *idx, uint32_t slots);
 int ensure_vtab(rg_index *idx, uint64_t words);
 uint32_t affordable_slots(rg_index *idx);
@@ -141,6 +144,18 @@ int knn_tc_max_norm(const float *sq, uint64_t n, float *d_out, cudaStream_t s);
 int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
                   int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
                   uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s);
+uint64_t knn_tc_seed_rows(uint64_t nb, uint32_t K);
+int knn_tc_seed(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t n_seed, uint32_t K,
+                int metric_l2, const float *qn, const float *bn, float bmax, float *seed_buf, float *tau, int sm_count,
+                cudaStream_t s);
+
+// device time per phase of the kNN calls of this thread since the last reset (filled only under RG_KNN_TRACE=1)
+struct KnnProfile {
+    double convert_base_ms = 0, convert_queries_ms = 0, seed_ms = 0, filter_ms = 0, merge_ms = 0;
+    uint64_t chunks = 0, overflow_retries = 0;
+};
+const KnnProfile &knn_last_profile();
+void knn_reset_profile();
 
 // BuildRoarGraph (rg_build.cu)
 int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, uint32_t knn_stride, uint32_t M_sq,
@@ -150,6 +165,12 @@ int adjacency_nnz_device(const uint32_t *d_adj, uint32_t stride, uint64_t nd, ui
 // exact kNN (rg_knn.cu)
 int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
                int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s);
+int knn_base_prepare(rg_knn_base *kb, const float *d_base, uint64_t nb, uint32_t dim, int metric, bool from_ws, cudaStream_t s);
+int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
+                    float *d_dists, cudaStream_t s);
+void knn_base_free(rg_knn_base *kb);
+// new object over device rows `d_base` (own_in: a device copy the object frees, or nullptr)
+int knn_base_new(rg_knn_base **out, const float *d_base, float *own_in, uint64_t nb, uint32_t dim, int metric);
 int topk_merge_device(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
                       float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s);
 

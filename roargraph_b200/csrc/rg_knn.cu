@@ -10,6 +10,7 @@
 // COSINE -> L2 on rows divided by their norm (:146-174).  Ties: earlier id wins (strict '>' at :214).
 #include <cfloat>
 #include <cstdio>
+#include <mutex>
 #include <vector>
 
 #include "rg_internal.h"
@@ -225,7 +226,7 @@ __device__ void merge_query_big(uint64_t q, unsigned long long *__restrict__ top
     for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) top[q * K + i] = sk[i];
     if (threadIdx.x == 0) {
         const unsigned long long kth = sk[K - 1];
-        tau[q] = (kth == ~0ull) ? INFINITY : ord2f((uint32_t)(kth >> 32));
+        if (kth != ~0ull) tau[q] = fminf(tau[q], ord2f((uint32_t)(kth >> 32)));  // tau only tightens (it may have been seeded)
         cand_cnt[2 * q] = 0;
         cand_cnt[2 * q + 1] = 0;
     }
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(128) knn_merge_fast_kernel(unsigned long long 
     if (threadIdx.x == 0) {
         if (kept) {
             const unsigned long long nk = sk[K - 1];
-            tau[q] = (nk == ~0ull) ? INFINITY : ord2f((uint32_t)(nk >> 32));
+            if (nk != ~0ull) tau[q] = fminf(tau[q], ord2f((uint32_t)(nk >> 32)));  // tau only tightens (it may have been seeded)
         }
         cand_cnt[2 * q] = 0;
         cand_cnt[2 * q + 1] = 0;
@@ -396,14 +397,13 @@ __global__ void topk_merge_kernel(const float *in_d, const uint32_t *in_i, uint3
     }
 }
 
-// Scratch buffers of knn_device live in a grow-only per-process workspace: cudaMalloc / cudaFree of the multi-GB
+// Scratch buffers of the kNN calls live in a grow-only per-device workspace: cudaMalloc / cudaFree of the multi-GB
 // candidate lists and the bf16 base copy cost ~10 % of a one-batch call, and a 10 M-query run re-enters with the same
-// sizes.  rg_knn_release_workspace() (knn_release_workspace) gives the memory back.
+// sizes.  rg_knn_release_workspace() (knn_release_workspace) gives the memory of the current device back.
 struct Workspace {
-    static constexpr int kSlots = 16;
+    static constexpr int kSlots = 20;
     void *p[kSlots] = {};
     size_t cap[kSlots] = {};
-    int device = -1;
     void release() {
         for (int i = 0; i < kSlots; ++i) {
             if (p[i]) cudaFree(p[i]);
@@ -412,12 +412,6 @@ struct Workspace {
         }
     }
     int get(int slot, size_t bytes, void **out) {
-        int dev = 0;
-        RG_CUDA(cudaGetDevice(&dev));
-        if (dev != device) {
-            release();
-            device = dev;
-        }
         if (cap[slot] < bytes) {
             if (p[slot]) cudaFree(p[slot]);
             p[slot] = nullptr;
@@ -429,19 +423,59 @@ struct Workspace {
         return RG_OK;
     }
 };
-Workspace g_ws;
-enum { WS_BN, WS_QN, WS_BCOPY, WS_QCOPY, WS_TOP, WS_CAND, WS_CNT, WS_TAU, WS_OVF, WS_B16, WS_Q16, WS_MAX, WS_WORK };
+constexpr int kMaxDevices = 64;
+Workspace g_ws[kMaxDevices];  // one per device: a workspace is only touched by calls running on its device (one at a time)
+enum { WS_BN, WS_QN, WS_BCOPY, WS_QCOPY, WS_TOP, WS_CAND, WS_CNT, WS_TAU, WS_OVF, WS_B16, WS_Q16, WS_MAX, WS_WORK, WS_SEED };
 
-struct Scratch {  // a view of one workspace slot
-    void *p = nullptr;
-};
-#define RG_WS(scr, slot, bytes)                                        \
-    do {                                                               \
-        int rc_ws_ = g_ws.get(slot, (size_t)(bytes), &(scr).p);        \
-        if (rc_ws_ != RG_OK) return rc_ws_;                            \
+Workspace *current_ws() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_ws[dev];
+}
+
+#define RG_WS(ws, ptr, slot, bytes)                                          \
+    do {                                                                     \
+        void *p_ws_ = nullptr;                                               \
+        int rc_ws_ = (ws)->get(slot, (size_t)(bytes), &p_ws_);               \
+        if (rc_ws_ != RG_OK) return rc_ws_;                                  \
+        (ptr) = reinterpret_cast<decltype(ptr)>(p_ws_);                      \
     } while (0)
 
+// RG_KNN_TRACE=1: device time of every phase (events + a stream synchronisation per phase: a diagnostic, never the timed path)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t s;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PhaseTimer(cudaStream_t st) : s(st) {
+        static const bool env = getenv("RG_KNN_TRACE") != nullptr;
+        on = env;
+        if (on) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+        }
+    }
+    ~PhaseTimer() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+    void begin() {
+        if (on) cudaEventRecord(e0, s);
+    }
+    void end(double &acc) {
+        if (!on) return;
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        acc += ms;
+    }
+};
+
+thread_local KnnProfile t_profile;
+
 }  // namespace
+
+const KnnProfile &knn_last_profile() { return t_profile; }
 
 static bool use_tensor_cores(uint32_t dim) {
     const char *m = getenv("RG_KNN_MODE");
@@ -449,143 +483,251 @@ static bool use_tensor_cores(uint32_t dim) {
     return knn_tc_supported(dim);
 }
 
-int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
-               int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s) {
-    if (!d_base || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
-    if (K == 0 || K > nb) { set_error("rg_knn: K must be in [1, nb]"); return RG_EINVAL; }
-    if (K > 1024) { set_error("rg_knn: K > 1024 not supported"); return RG_EINVAL; }
+}  // namespace rg
+
+// The base side of exact_knn, prepared once for any number of query batches (compute_groundtruth walks the queries
+// 1 024 at a time against a base part it keeps in memory, compute_groundtruth.cpp:187-200): squared norms, the
+// normalised copy for COSINE (:146-174), the bf16 copy and max norm for the tensor-core filter.
+struct rg_knn_base {
+    const float *in = nullptr;  // caller's rows (device)
+    float *own_in = nullptr;    // device copy of host rows (rg_knn_base_create with a host pointer)
+    uint64_t nb = 0;
+    uint32_t dim = 0;
+    int metric = 0, metric_l2 = 0, device = 0;
+    bool tc = false, from_ws = false;
+    const float *B = nullptr;  // rows the distances are computed on (the normalised copy for COSINE)
+    float *bcopy = nullptr, *bn = nullptr;
+    void *b16 = nullptr;
+    float bmax = 0.f;
+};
+
+namespace rg {
+
+void knn_base_free(rg_knn_base *kb) {
+    if (!kb) return;
+    if (!kb->from_ws) {
+        if (kb->bcopy) cudaFree(kb->bcopy);
+        if (kb->bn) cudaFree(kb->bn);
+        if (kb->b16) cudaFree(kb->b16);
+    }
+    if (kb->own_in) cudaFree(kb->own_in);
+    delete kb;
+}
+
+int knn_base_new(rg_knn_base **out, const float *d_base, float *own_in, uint64_t nb, uint32_t dim, int metric) {
+    rg_knn_base *kb = new rg_knn_base();
+    kb->own_in = own_in;
+    int rc = knn_base_prepare(kb, d_base, nb, dim, metric, /*from_ws=*/false, nullptr);
+    if (rc != RG_OK) {
+        knn_base_free(kb);
+        return rc;
+    }
+    *out = kb;
+    return RG_OK;
+}
+
+// from_ws: the derived arrays live in the per-device workspace (one-shot rg_knn_dev calls), else in their own allocations
+int knn_base_prepare(rg_knn_base *kb, const float *d_base, uint64_t nb, uint32_t dim, int metric, bool from_ws, cudaStream_t s) {
+    if (!d_base || nb == 0 || dim == 0) { set_error("rg_knn: null/empty base"); return RG_EINVAL; }
     if (nb >= 0x7fffffffull) { set_error("rg_knn: nb must be < 2^31 per call (the reference uses int ids)"); return RG_EINVAL; }
-    if (nq == 0) return RG_OK;
     const bool cosine = metric == RG_METRIC_COSINE;
     const int metric_l2 = (metric == RG_METRIC_L2 || cosine) ? 1 : 0;
     if (!metric_l2 && metric != RG_METRIC_INNER_PRODUCT) { set_error("rg_knn: unknown metric"); return RG_EINVAL; }
+    RG_CUDA(cudaGetDevice(&kb->device));
+    kb->in = d_base;
+    kb->nb = nb;
+    kb->dim = dim;
+    kb->metric = metric;
+    kb->metric_l2 = metric_l2;
+    kb->tc = use_tensor_cores(dim);
+    kb->from_ws = from_ws;
+    kb->B = d_base;
+    Workspace *ws = current_ws();
+    if (!ws) { set_error("rg_knn: no current CUDA device"); return RG_ECUDA; }
+    PhaseTimer pt(s);
+    pt.begin();
+    if (metric_l2 || kb->tc) {  // the tensor-core filter needs the norms for its error bound even for inner product
+        if (from_ws) RG_WS(ws, kb->bn, WS_BN, nb * sizeof(float));
+        else RG_CUDA(cudaMalloc(&kb->bn, nb * sizeof(float)));
+        row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(d_base, nb, dim, kb->bn);
+        if (cosine) {
+            if (from_ws) RG_WS(ws, kb->bcopy, WS_BCOPY, nb * dim * sizeof(float));
+            else RG_CUDA(cudaMalloc(&kb->bcopy, nb * dim * sizeof(float)));
+            row_normalize_kernel<<<(unsigned)((nb * dim + 255) / 256), 256, 0, s>>>(d_base, nb, dim, kb->bn, kb->bcopy);
+            kb->B = kb->bcopy;
+            row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(kb->B, nb, dim, kb->bn);  // :170-171 recompute
+        }
+    }
+    if (kb->tc) {
+        const uint32_t kp = knn_tc_pitch(dim);
+        if (from_ws) RG_WS(ws, kb->b16, WS_B16, nb * kp * 2);
+        else RG_CUDA(cudaMalloc(&kb->b16, nb * kp * 2));
+        float *d_max = nullptr;
+        RG_WS(ws, d_max, WS_MAX, sizeof(float));
+        int rc = knn_tc_convert(kb->B, nb, dim, kb->b16, nullptr, s);
+        if (rc != RG_OK) return rc;
+        if ((rc = knn_tc_max_norm(kb->bn, nb, d_max, s)) != RG_OK) return rc;
+        float m2 = 0.f;
+        RG_CUDA(cudaMemcpyAsync(&m2, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+        RG_CUDA(cudaStreamSynchronize(s));
+        kb->bmax = sqrtf(m2);
+    }
+    RG_CUDA(cudaGetLastError());
+    pt.end(t_profile.convert_base_ms);
+    return RG_OK;
+}
 
-    const bool tc = use_tensor_cores(dim);
+// One or more query batches against a prepared base.  tau_seed (optional, device, nq floats): an externally known upper
+// bound of every query's K-th best distance (e.g. agreed between the shards of a sharded base); the ramp then starts from it.
+int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
+                    float *d_dists, cudaStream_t s) {
+    if (!kb || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
+    const uint64_t nb = kb->nb;
+    const uint32_t dim = kb->dim;
+    if (K == 0 || K > nb) { set_error("rg_knn: K must be in [1, nb]"); return RG_EINVAL; }
+    if (K > 1024) { set_error("rg_knn: K > 1024 not supported"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    {
+        int dev = 0;
+        RG_CUDA(cudaGetDevice(&dev));
+        if (dev != kb->device) RG_CUDA(cudaSetDevice(kb->device));
+    }
+    Workspace *ws = current_ws();
+    if (!ws) { set_error("rg_knn: no current CUDA device"); return RG_ECUDA; }
+    const bool cosine = kb->metric == RG_METRIC_COSINE;
+    const int metric_l2 = kb->metric_l2;
+    const bool tc = kb->tc;
+    const int sms = sm_count();
     const uint32_t cap = std::max<uint32_t>(2048u, 4u * K);
-    // first chunk: everything survives (tau = inf), so keep it small on the tensor-core path (one 256-row tile);
-    // chunks then double, which keeps the expected survivors per chunk near K
+    // seed pass (tensor-core path, large bases): tau starts from a bound derived from the bf16 scores of the first rows
+    // alone; otherwise the first chunk is small because everything in it survives (tau = inf) and chunks then grow so that
+    // the expected survivors per chunk stay near K
+    const uint64_t n_seed = tc ? knn_tc_seed_rows(nb, K) : 0;
     const uint64_t chunk0 = tc ? 256u : cap;
     uint32_t sort_n = 1;
     while (sort_n < cap + K) sort_n <<= 1;
     // query batches so that the candidate lists stay within ~2 GiB
     uint64_t qb_max = std::max<uint64_t>(TQ, ((2ull << 30) / (cap * 8ull)) / TQ * TQ);
     if (tc) {  // whole waves of the tensor-core filter: one CTA = 256 queries, one CTA per SM
-        const uint64_t wave = (uint64_t)sm_count() * 256u;
+        const uint64_t wave = (uint64_t)sms * 256u;
         const uint64_t fit = ((2600ull << 20) / (cap * 8ull)) / wave * wave;
         if (fit) qb_max = fit;
     }
+    const uint64_t qb_alloc = std::min<uint64_t>(nq, qb_max);
+    PhaseTimer pt(s);
 
-    Scratch s_bn, s_qn, s_bcopy, s_qcopy, s_top, s_cand, s_cnt, s_tau, s_ovf, s_b16, s_q16, s_max, s_work;
-    float *bn = nullptr, *qn = nullptr;
-    const float *B = d_base, *Q = d_queries;
-    if (metric_l2 || tc) {  // the tensor-core filter needs the norms for its error bound even for inner product
-        RG_WS(s_bn, WS_BN, nb * sizeof(float));
-        RG_WS(s_qn, WS_QN, nq * sizeof(float));
-        bn = (float *)s_bn.p;
-        qn = (float *)s_qn.p;
-        row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(d_base, nb, dim, bn);
+    float *qn = nullptr, *qcopy = nullptr;
+    const float *Q = d_queries;
+    pt.begin();
+    if (metric_l2 || tc) {
+        RG_WS(ws, qn, WS_QN, nq * sizeof(float));
         row_sqnorm_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(d_queries, nq, dim, qn);
         if (cosine) {
-            RG_WS(s_bcopy, WS_BCOPY, nb * dim * sizeof(float));
-            RG_WS(s_qcopy, WS_QCOPY, nq * dim * sizeof(float));
-            row_normalize_kernel<<<(unsigned)((nb * dim + 255) / 256), 256, 0, s>>>(d_base, nb, dim, bn, (float *)s_bcopy.p);
-            row_normalize_kernel<<<(unsigned)((nq * dim + 255) / 256), 256, 0, s>>>(d_queries, nq, dim, qn, (float *)s_qcopy.p);
-            B = (const float *)s_bcopy.p;
-            Q = (const float *)s_qcopy.p;
-            row_sqnorm_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, s>>>(B, nb, dim, bn);  // :170-171 recompute
+            RG_WS(ws, qcopy, WS_QCOPY, nq * dim * sizeof(float));
+            row_normalize_kernel<<<(unsigned)((nq * dim + 255) / 256), 256, 0, s>>>(d_queries, nq, dim, qn, qcopy);
+            Q = qcopy;
             row_sqnorm_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(Q, nq, dim, qn);
         }
     }
-    const uint64_t qb_alloc = std::min<uint64_t>(nq, qb_max);
-    float bmax = 0.f;
+    void *q16 = nullptr;
+    float *seed_buf = nullptr;
     if (tc) {
-        const uint32_t kp = knn_tc_pitch(dim);
-        RG_WS(s_b16, WS_B16, nb * kp * 2);
-        RG_WS(s_q16, WS_Q16, qb_alloc * kp * 2);
-        RG_WS(s_max, WS_MAX, sizeof(float));
-        int rc = knn_tc_convert(B, nb, dim, s_b16.p, nullptr, s);
-        if (rc != RG_OK) return rc;
-        if ((rc = knn_tc_max_norm(bn, nb, (float *)s_max.p, s)) != RG_OK) return rc;
-        float m2 = 0.f;
-        RG_CUDA(cudaMemcpyAsync(&m2, s_max.p, sizeof(float), cudaMemcpyDeviceToHost, s));
-        RG_CUDA(cudaStreamSynchronize(s));
-        bmax = sqrtf(m2);
+        RG_WS(ws, q16, WS_Q16, qb_alloc * knn_tc_pitch(dim) * 2);
+        if (n_seed) RG_WS(ws, seed_buf, WS_SEED, (n_seed / 128u) * qb_alloc * sizeof(float));
     }
+    pt.end(t_profile.convert_queries_ms);
     Rerank rr{};
     if (tc) {
-        rr.base = B;
+        rr.base = kb->B;
         rr.qn = qn;
-        rr.bn = bn;
+        rr.bn = kb->bn;
         rr.dim = dim;
         rr.metric_l2 = metric_l2;
     }
     const size_t merge_smem = (size_t)sort_n * 8 + (tc ? (size_t)dim * 4 : 0);
-    RG_WS(s_top, WS_TOP, qb_alloc * K * sizeof(unsigned long long));
-    RG_WS(s_cand, WS_CAND, qb_alloc * cap * sizeof(unsigned long long));
-    RG_WS(s_cnt, WS_CNT, 2 * qb_alloc * sizeof(uint32_t));
-    RG_WS(s_work, WS_WORK, (qb_alloc + 1) * sizeof(uint32_t));
-    RG_WS(s_tau, WS_TAU, qb_alloc * sizeof(float));
-    RG_WS(s_ovf, WS_OVF, sizeof(uint32_t));
-    unsigned long long *top = (unsigned long long *)s_top.p, *cand = (unsigned long long *)s_cand.p;
-    uint32_t *cnt = (uint32_t *)s_cnt.p, *ovf = (uint32_t *)s_ovf.p;
-    float *tau = (float *)s_tau.p;
+    unsigned long long *top = nullptr, *cand = nullptr;
+    uint32_t *cnt = nullptr, *ovf = nullptr, *worklist = nullptr;
+    float *tau = nullptr;
+    RG_WS(ws, top, WS_TOP, qb_alloc * K * sizeof(unsigned long long));
+    RG_WS(ws, cand, WS_CAND, qb_alloc * cap * sizeof(unsigned long long));
+    RG_WS(ws, cnt, WS_CNT, 2 * qb_alloc * sizeof(uint32_t));
+    RG_WS(ws, worklist, WS_WORK, (qb_alloc + 1) * sizeof(uint32_t));
+    RG_WS(ws, tau, WS_TAU, qb_alloc * sizeof(float));
+    RG_WS(ws, ovf, WS_OVF, sizeof(uint32_t));
     RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
     uint32_t fast_sn = 1024;
     while (fast_sn < 4u * K) fast_sn <<= 1;
     if (fast_sn > sort_n) fast_sn = sort_n;
     const size_t fast_smem = (size_t)fast_sn * 8 + (size_t)dim * 4;
-    const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
+    const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(kb->B) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
     RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
     RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-    uint32_t *worklist = (uint32_t *)s_work.p, *work_cnt = worklist + qb_alloc;
+    uint32_t *work_cnt = worklist + qb_alloc;
 
     for (uint64_t qs = 0; qs < nq; qs += qb_max) {
         const uint64_t nqb = std::min<uint64_t>(qb_max, nq - qs);
         if (tc) {
-            int rc = knn_tc_convert(Q + qs * dim, nqb, dim, s_q16.p, nullptr, s);
+            pt.begin();
+            int rc = knn_tc_convert(Q + qs * dim, nqb, dim, q16, nullptr, s);
             if (rc != RG_OK) return rc;
+            pt.end(t_profile.convert_queries_ms);
             rr.queries = Q + qs * dim;
             rr.qn = qn + qs;
         }
         for (int attempt = 0; attempt < 2; ++attempt) {
-            // attempt 0: chunks double in size (expected survivors per chunk ~K); attempt 1 (after a candidate-list
-            // overflow): every chunk has at most `cap` rows, which cannot overflow.
+            // attempt 0: seeded tau (or tau = inf and a 256-row first chunk), chunks growing with the rows seen (expected
+            // survivors per chunk ~K); attempt 1 (after a candidate-list overflow): every chunk has at most `cap` rows,
+            // which cannot overflow.
             const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
             knn_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, s>>>(top, nqb * K, tau, cnt, nqb);
             RG_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), s));
-            uint64_t lo = 0, csize = attempt == 0 ? chunk0 : (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap);
+            const bool seeded = attempt == 0 && n_seed != 0;
+            if (seeded) {
+                pt.begin();
+                int rc = knn_tc_seed(q16, nqb, kb->b16, nb, dim, n_seed, K, metric_l2, qn + qs, kb->bn, kb->bmax, seed_buf, tau, sms, s);
+                if (rc != RG_OK) return rc;
+                pt.end(t_profile.seed_ms);
+            }
+            uint64_t lo = 0;
+            uint64_t csize = attempt == 1 ? (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap) : (seeded ? n_seed : chunk0);
             while (lo < nb) {
                 const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
+                pt.begin();
                 if (tc) {
-                    int rc = knn_tc_filter(s_q16.p, nqb, s_b16.p, nb, dim, lo, hi, metric_l2, tau, qn + qs, bn, bmax, cand, cnt, cap,
-                                           ovf, sm_count(), s);
+                    int rc = knn_tc_filter(q16, nqb, kb->b16, nb, dim, lo, hi, metric_l2, tau, qn + qs, kb->bn, kb->bmax, cand, cnt, cap,
+                                           ovf, sms, s);
                     if (rc != RG_OK) return rc;
                 } else {
                     dim3 grid((unsigned)((hi - lo + TB - 1) / TB), (unsigned)((nqb + TQ - 1) / TQ));
-                    knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
-                                                                        bn, metric_l2, tau, cand, cnt, cap, ovf);
+                    knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, kb->B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
+                                                                        kb->bn, metric_l2, tau, cand, cnt, cap, ovf);
                 }
+                pt.end(t_profile.filter_ms);
+                pt.begin();
                 if (tc) {
                     // fast path per query, then the general kernel over the (normally empty) work list of long lists
                     RG_CUDA(cudaMemsetAsync(work_cnt, 0, sizeof(uint32_t), s));
                     if (vec) knn_merge_fast_kernel<true><<<(unsigned)nqb, 128, fast_smem, s>>>(top, K, cand, cnt, cap, tau, fast_sn, rr, worklist, work_cnt);
                     else knn_merge_fast_kernel<false><<<(unsigned)nqb, 128, fast_smem, s>>>(top, K, cand, cnt, cap, tau, fast_sn, rr, worklist, work_cnt);
-                    knn_merge_kernel<<<(unsigned)std::min<uint64_t>(nqb, 2ull * sm_count()), 256, merge_smem, s>>>(
+                    knn_merge_kernel<<<(unsigned)std::min<uint64_t>(nqb, 2ull * sms), 256, merge_smem, s>>>(
                         top, K, cand, cnt, cap, tau, sort_n, rr, worklist, work_cnt);
                 } else {
                     knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr, nullptr, nullptr);
                 }
+                pt.end(t_profile.merge_ms);
+                t_profile.chunks += 1;
                 lo = hi;
                 // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
-                // still fit in L2 (tensor-core path: the re-rank gather of those ~3K survivors never reaches DRAM, and
-                // the fixed per-launch cost of filter + merge dominates there)
-                if (attempt == 0) csize = std::min<uint64_t>((tc && lo < 65536) ? 3 * lo : lo, 1ull << 22);
+                // still fit in L2 (tensor-core path without a seed: the re-rank gather of those ~3K survivors never reaches
+                // DRAM, and the fixed per-launch cost of filter + merge dominates there)
+                if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && lo < 65536) ? 3 * lo : lo, 1ull << 22);
             }
             RG_CUDA(cudaGetLastError());
             uint32_t h_ovf = 0;
             RG_CUDA(cudaMemcpyAsync(&h_ovf, ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             RG_CUDA(cudaStreamSynchronize(s));
             if (!h_ovf) break;
+            t_profile.overflow_retries += 1;
             if (attempt == 1) { set_error("rg_knn: candidate overflow in safe mode (internal error)"); return RG_ENOMEM; }
         }
         knn_unpack_kernel<<<(unsigned)((nqb * K + 255) / 256), 256, 0, s>>>(top, nqb * K, id_offset, d_ids + qs * K, d_dists + qs * K);
@@ -595,7 +737,24 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     return RG_OK;
 }
 
-void knn_release_workspace() { g_ws.release(); }
+int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
+               int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s) {
+    if (!d_base || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
+    if (K == 0 || K > nb) { set_error("rg_knn: K must be in [1, nb]"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    t_profile = KnnProfile{};
+    rg_knn_base *kb = new rg_knn_base();
+    int rc = knn_base_prepare(kb, d_base, nb, dim, metric, /*from_ws=*/true, s);
+    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s);
+    knn_base_free(kb);
+    return rc;
+}
+
+void knn_reset_profile() { t_profile = KnnProfile{}; }
+
+void knn_release_workspace() {
+    if (Workspace *ws = current_ws()) ws->release();
+}
 
 int topk_merge_device(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
                       float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s) {

@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -238,6 +239,10 @@ struct TcParams {
     uint32_t *cand_cnt;
     uint32_t cap;
     uint32_t *overflow;
+    // seed pass (knn_tc_seed): instead of scanning for survivors every epilogue thread stores the maximum of its 128 columns
+    // of each tile, seed_out[((tile - tile_lo) * 2 + half) * seed_stride + query]
+    float *seed_out;
+    uint64_t seed_stride;
 };
 
 // NQT = query tiles per CTA.  NQT == 2 (dim <= 256): 256 queries share every base tile, which halves the L2 -> SM operand
@@ -469,6 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_filter_kernel(const __grid
 constexpr int kPairN = 256;                                    // UMMA N of the pair = base rows per tile
 constexpr uint32_t kPairBBytesPerKb = (kPairN / 2) * kBlockK * 2;  // each CTA stages half of the tile's rows: 16 KB
 
+template <bool kSeed>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     knn_tc_filter_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
     constexpr uint32_t kIdesc = make_idesc(kPairN, 2 * kBlockM);
@@ -623,6 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + buf * kAccCols + half * 128u;
             uint32_t r[2][32];
+            float tile_max = -INFINITY;  // seed pass only
             __syncwarp();
             tc_ld32(taddr, r[0]);
 #pragma unroll
@@ -646,7 +653,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rr[e]);
                 }
                 float gmax[4];
-                if (max32(v, gmax) > theta) {  // rare once tau has tightened
+                if (kSeed) {
+                    tile_max = fmaxf(tile_max, max32(v, gmax));
+                } else if (max32(v, gmax) > theta) {  // rare once tau has tightened
                     uint32_t mask = survivor_mask(v, gmax, theta);
                     while (mask) {
                         const int e = __ffs(mask) - 1;
@@ -670,8 +679,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+            // seed pass: one value per (tile, column half, query); consecutive lanes = consecutive queries -> 128-byte stores
+            if (kSeed && qrow < p.nq) p.seed_out[(uint64_t)((tile - p.tile_lo) * 2u + half) * p.seed_stride + qrow] = tile_max;
         }
-        if (!p.atomic_append && qrow < p.nq && cnt) p.cand_cnt[2 * qrow + half] = cnt;
+        if (!kSeed && !p.atomic_append && qrow < p.nq && cnt) p.cand_cnt[2 * qrow + half] = cnt;
     }
     tc_fence_before();
     cluster_sync_all();
@@ -817,11 +828,120 @@ static int launch_filter_pair(const void *q_bf16, uint64_t nq, const void *b_bf1
     splits = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     p.atomic_append = splits > 1 ? 1 : 0;
     const size_t smem = fixed + (size_t)stages * kPairBBytesPerKb;
-    RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(q_ctas, splits);
-    knn_tc_filter_pair_kernel<<<grid, kThreads, smem, s>>>(map_q, map_b, p);
+    if (p.seed_out) {
+        RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_tc_filter_pair_kernel<true><<<grid, kThreads, smem, s>>>(map_q, map_b, p);
+    } else {
+        RG_CUDA(cudaFuncSetAttribute(knn_tc_filter_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_tc_filter_pair_kernel<false><<<grid, kThreads, smem, s>>>(map_q, map_b, p);
+    }
     RG_CUDA(cudaGetLastError());
     return RG_OK;
+}
+
+// |dot_bf16 - dot| <= kErrRel * ||q|| * ||b||: (2u + u^2) with u = 2^-8 (bf16 round-to-nearest), plus slack for the fp32 accumulation
+constexpr float kErrRel = 1.01f * 0.0078125f;
+
+namespace {
+__device__ __forceinline__ uint32_t seed_f2ord(float f) {  // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float seed_ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// tau seed: the K-th largest of a query's G group maxima (each the bf16 score of a DISTINCT base row) bounds the K-th best
+// distance over the seed rows from above once the bf16 error bound is added.  One CTA = 32 queries, staged through shared
+// memory ([g][query] in global memory: the filter kernel's stores are coalesced over queries); one warp = one query at a
+// time, 32-step radix select over the order-preserving keys (G <= 1024 values, up to 32 per lane).
+constexpr int kSeedMaxPerLane = 32;
+__global__ void __launch_bounds__(256) knn_seed_select_kernel(const float *__restrict__ seed, uint64_t seed_stride, uint32_t G,
+                                                              uint64_t nq, uint32_t K, int metric_l2, const float *__restrict__ qn,
+                                                              float bmax, float *__restrict__ tau) {
+    extern __shared__ float s_tile[];  // G x 33
+    const uint64_t q0 = (uint64_t)blockIdx.x * 32u;
+    for (uint32_t i = threadIdx.x; i < G * 32u; i += blockDim.x) {
+        const uint32_t g = i >> 5, c = i & 31u;
+        s_tile[g * 33u + c] = (q0 + c < nq) ? seed[(uint64_t)g * seed_stride + q0 + c] : -INFINITY;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t c = warp; c < 32u; c += blockDim.x >> 5) {
+        const uint64_t q = q0 + c;
+        if (q >= nq) break;
+        uint32_t key[kSeedMaxPerLane];
+#pragma unroll
+        for (int j = 0; j < kSeedMaxPerLane; ++j) {
+            const uint32_t g = (uint32_t)lane + 32u * j;
+            key[j] = g < G ? seed_f2ord(s_tile[g * 33u + c]) : 0u;  // 0 = below every real key
+        }
+        uint32_t prefix = 0, remaining = K;
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t want = prefix | (1u << b), mask = ~((1u << b) - 1u);
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kSeedMaxPerLane; ++j) cnt += ((key[j] & mask) == want) ? 1u : 0u;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt >= remaining) prefix = want;
+            else remaining -= cnt;
+        }
+        if (lane == 0) {
+            const float vk = seed_ord2f(prefix);  // K-th largest bf16 score (IP: dot; L2: 2 dot - ||b||^2)
+            const float qq = qn[q];
+            const float E = kErrRel * sqrtf(qq) * bmax;
+            // K distinct rows have a TRUE internal distance <= this value; 1e-30: a zero query (E = 0, all scores equal) keeps
+            // every row instead of none
+            float t = metric_l2 ? (qq - vk) + 2.f * E : (-vk) + E;
+            t += fmaxf(fabsf(t) * 1e-6f, 1e-30f);
+            tau[q] = t;
+        }
+    }
+}
+}  // namespace
+
+// Seed pass over base rows [0, n_seed) (a multiple of 256): tau[q] <- an upper bound of the K-th best distance of query q
+// over those rows, from the tensor-core scores alone (no candidate lists, no re-rank).  seed_buf: 2 * n_seed / 256 * nq floats.
+int knn_tc_seed(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t n_seed, uint32_t K,
+                int metric_l2, const float *qn, const float *bn, float bmax, float *seed_buf, float *tau, int sm_count,
+                cudaStream_t s) {
+    const uint32_t kp = knn_tc_pitch(dim);
+    const uint32_t G = (uint32_t)(n_seed / 128u);
+    if (n_seed == 0 || n_seed % 256u != 0 || n_seed > nb || G < K || G > 32u * kSeedMaxPerLane) {
+        set_error("rg_knn: bad seed range (internal error)");
+        return RG_EINVAL;
+    }
+    TcParams p{};
+    p.nq = nq;
+    p.nb = nb;
+    p.num_kb = (kp + kBlockK - 1) / kBlockK;
+    p.ksteps_last = ((kp - (p.num_kb - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
+    p.metric_l2 = metric_l2;
+    p.tau = tau;  // read but unused by the seed kernel
+    p.qn = qn;
+    p.bn = bn;
+    p.bmax = bmax;
+    p.err_rel = kErrRel;
+    p.seed_out = seed_buf;
+    p.seed_stride = nq;
+    int rc = launch_filter_pair(q_bf16, nq, b_bf16, nb, kp, 0, n_seed, p, sm_count, s);
+    if (rc != RG_OK) return rc;
+    const size_t smem = (size_t)G * 33u * sizeof(float);
+    RG_CUDA(cudaFuncSetAttribute(knn_seed_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_seed_select_kernel<<<(unsigned)((nq + 31) / 32), 256, smem, s>>>(seed_buf, nq, G, nq, K, metric_l2, qn, bmax, tau);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+// rows of the seed pass for a base of nb rows and top-K (0: too small to seed — the chunk ramp starts from tau = inf)
+uint64_t knn_tc_seed_rows(uint64_t nb, uint32_t K) {
+    const char *force = getenv("RG_KNN_QTILES");
+    if (force && (force[0] == '1' || force[0] == '2')) return 0;  // only the 2-CTA kernel has the seed epilogue
+    if (const char *v = getenv("RG_KNN_SEED")) {
+        if (v[0] == '0') return 0;
+    }
+    uint64_t n = std::min<uint64_t>(65536u, (nb / 4u) / 256u * 256u);
+    if (n / 128u < 2ull * K) return 0;  // the K-th of fewer than 2K group maxima is a poor bound
+    return n;
 }
 
 int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
@@ -842,7 +962,7 @@ int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t 
     p.cand_cnt = cand_cnt;
     p.cap = cap;
     p.overflow = overflow;
-    p.err_rel = 1.01f * 0.0078125f;  // (2u + u^2) with u = 2^-8 (bf16 round-to-nearest), plus slack for the fp32 accumulation
+    p.err_rel = kErrRel;
     // RG_KNN_QTILES=1|2 selects the single-CTA kernels (one or two resident query tiles); default: the 2-CTA kernel
     const char *force = getenv("RG_KNN_QTILES");
     if (!force || (force[0] != '1' && force[0] != '2'))

@@ -74,10 +74,14 @@ def main():
                                      "--learn_base_nn_path", kf, "--M_sq", "100", "--M_pjbp", "35", "--L_pjpq", "500",
                                      "-T", str(a.threads)], stdout=lf, stderr=subprocess.STDOUT)
     csv = os.path.join(out, "sweep.csv")
-    timing["search_s"] = run([os.path.join(REF, "ref_test_search_roargraph"), "--data_type", "float", "--dist", a.dist,
+    for ln in (open(os.path.join(out, "build.log")) if os.path.exists(os.path.join(out, "build.log")) else []):
+        if ln.startswith("indexing time:"):
+            timing["build_indexing_s"] = float(ln.split(":")[1])
+    if not os.path.exists(csv):
+        timing["search_s"] = run([os.path.join(REF, "ref_test_search_roargraph"), "--data_type", "float", "--dist", a.dist,
                               "--base_data_path", bf, "--query_path", qf, "--gt_path", gf, "--projection_index_save_path", xf,
                               "--k", "10", "-T", str(a.threads), "--evaluation_save_path", csv, "--L_pq"]
-                             + [str(L) for L in README_L_SWEEP], stdout=subprocess.DEVNULL)
+                                 + [str(L) for L in README_L_SWEEP], stdout=subprocess.DEVNULL)
     ep, row_off, nbrs = F.read_projection_index(xf)
     deg = np.diff(row_off.astype(np.int64))
     rows = [ln.strip().split(",") for ln in open(csv) if ln.strip()]
@@ -87,9 +91,9 @@ def main():
         "M_sq": 100, "M_pjbp": 35, "L_pjpq": 500, "ep": int(ep), "avg_degree": float(deg.mean()),
         "max_degree": int(deg.max()), "min_degree": int(deg.min()),
         "degree_hist": np.bincount(deg, minlength=int(deg.max()) + 1).tolist(),
-        # CSV columns: L_pq,qps,avg_cmps,ms_per_query,recall,rderr,avg_hops  (tests/test_search_roargraph.cpp:234-235)
+        # CSV columns: L_pq,qps,avg_cmps,ms_per_query,recall,avg_hops  (tests/test_search_roargraph.cpp:234-235)
         "sweep": [{"L_pq": int(r[0]), "qps": float(r[1]), "avg_cmps": float(r[2]), "recall": float(r[4]),
-                   "avg_hops": float(r[6])} for r in rows],
+                   "avg_hops": float(r[-1])} for r in rows],
         "timing": timing,
     }
     dst = os.path.join(ROOT, "tests", "golden", f"ref_build_{a.tag}_stats.json")
