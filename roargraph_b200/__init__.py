@@ -236,6 +236,18 @@ class RoarIndex:
                                          _np_ptr(dists), _np_ptr(cmps), _np_ptr(hops)))
         return ids, dists, cmps, hops
 
+    def search_bipartite_dev(self, d_q, k: int, L_pq: int, d_ids, d_dists, d_cmps=None, d_hops=None, d_init_ids=None,
+                             n_init: int = 10, seed: int = 0, stream=None) -> None:
+        """Device tensors, asynchronous on `stream`; d_init_ids: int32/uint32 [nq, n_init] or None (seeded draw)."""
+        if d_init_ids is not None:
+            n_init = d_init_ids.shape[1]
+        _check(lib().rg_search_bipartite_dev(self._h, C.c_void_p(d_q.data_ptr()), d_q.shape[0], k, L_pq,
+                                             C.c_void_p(d_init_ids.data_ptr()) if d_init_ids is not None else None,
+                                             n_init, seed, C.c_void_p(d_ids.data_ptr()), C.c_void_p(d_dists.data_ptr()),
+                                             C.c_void_p(d_cmps.data_ptr()) if d_cmps is not None else None,
+                                             C.c_void_p(d_hops.data_ptr()) if d_hops is not None else None,
+                                             _stream_ptr(stream)))
+
     # -- accounting --------------------------------------------------------------------------------------------
     def last_stats(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -468,15 +468,34 @@ __device__ __forceinline__ uint32_t filter_unvisited_ids(WarpCtx &w, uint8_t *ta
     __syncwarp();
     return ncand;
 }
-__device__ __forceinline__ uint32_t filter_unvisited(WarpCtx &w, uint8_t *tags, uint8_t epoch, const uint32_t *list,
-                                                     uint32_t cnt, uint32_t ncand, uint32_t exclude = 0xffffffffu) {
+// cand[0..n) -> its distinct ids, first occurrences kept in order; returns their number.  The visited filter above reads all
+// tags of a 96-id batch before it writes any, so an id that occurs twice inside one batch passes twice; adjacency rows are
+// duplicate-free by construction (deduplicated at upload), the concatenated second-hop lists of the bipartite search are not.
+__device__ __forceinline__ uint32_t dedupe_fresh(WarpCtx &w, uint32_t n) {
+    const int lane = w.lane;
     uint32_t id[3];
+    bool keep[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const uint32_t i = j * 32 + w.lane;
-        id[j] = i < cnt ? __ldg(list + i) : 0u;
+    for (int r = 0; r < 3; ++r) {
+        const uint32_t i = r * 32 + lane;
+        keep[r] = i < n;
+        id[r] = keep[r] ? w.cand[i] : 0u;
+        const uint32_t lim = min(n, (uint32_t)(r * 32 + 31));  // entries before the last lane of this row
+        for (uint32_t j = 0; j < lim; ++j) {                    // every lane reads cand[j]: a broadcast
+            const uint32_t c = w.cand[j];
+            if (j < i && c == id[r]) keep[r] = false;
+        }
     }
-    return filter_unvisited_ids(w, tags, epoch, id, cnt, ncand, exclude);
+    __syncwarp();  // every read precedes the compaction writes
+    uint32_t m = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint32_t b = __ballot_sync(kFull, keep[r]);
+        if (keep[r]) w.cand[m + __popc(b & ((1u << lane) - 1u))] = id[r];
+        m += __popc(b);
+    }
+    __syncwarp();
+    return m;
 }
 
 // ---- visited table --------------------------------------------------------------------------------------------------------
@@ -757,26 +776,55 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                     }
                 }
             } else {
-                // two-hop expansion through the query nodes (:324-341); hops++ precedes the empty-adjacency skip (:320-323)
-                const uint64_t b = p.row_off[u], e = p.row_off[u + 1];
+                // Two-hop expansion through the query nodes (:324-341), flattened: the current node's query-node list is read
+                // cooperatively (one id per lane), every lane fetches the CSR bounds of its query node in ONE round trip, and the
+                // concatenation of the second-hop lists streams through the visited filter 96 ids at a time exactly like a
+                // RoarGraph adjacency row — instead of one dependent row_off / id / tag / row chain per query node.  The
+                // reference walks the lists one after the other; the order inside a hop is unobservable, and an
+                // id that sits in several lists of the hop is evaluated once here as there (the visited array there, the
+                // visited filter + dedupe_fresh here).  hops++ precedes the empty-adjacency skip (:320-323).
+                const uint64_t b = __ldg(p.row_off + u), e = __ldg(p.row_off + u + 1);
                 adjw += (uint32_t)(e - b);
-                uint32_t ncand = 0;
-                for (uint64_t j = b; j < e; ++j) {
-                    const uint32_t nbr = __ldg(p.csr_nbrs + j);
-                    const uint64_t b2 = p.row_off[nbr], e2 = p.row_off[nbr + 1];
-                    adjw += (uint32_t)(e2 - b2);
-                    for (uint64_t off = b2; off < e2; off += 32) {
-                        if (ncand + 32 > (uint32_t)kCandCap) {
-                            cmps += ncand;
-                            evaluate<kL2>(w, p, ncand, false);
-                            ncand = 0;
-                        }
-                        ncand = filter_unvisited(w, tags, (uint8_t)epoch, p.csr_nbrs + off, (uint32_t)min((uint64_t)32, e2 - off), ncand);
+                for (uint64_t c0 = b; c0 < e; c0 += 32) {
+                    const uint32_t nqn = (uint32_t)min((uint64_t)32, e - c0);
+                    uint64_t b2 = 0;
+                    uint32_t len = 0;
+                    if ((uint32_t)lane < nqn) {
+                        const uint32_t nbr = __ldg(p.csr_nbrs + c0 + lane);
+                        b2 = __ldg(p.row_off + nbr);
+                        len = (uint32_t)(__ldg(p.row_off + nbr + 1) - b2);
                     }
-                }
-                if (ncand) {
-                    cmps += ncand;
-                    evaluate<kL2>(w, p, ncand, false);
+                    uint32_t incl = len;  // inclusive prefix sum of the list lengths over the lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const uint32_t start = incl - len;
+                    const uint32_t total = __shfl_sync(kFull, incl, 31);
+                    adjw += total;
+                    for (uint32_t p0 = 0; p0 < total; p0 += kCandCap) {
+                        const uint32_t cnt = min(total - p0, (uint32_t)kCandCap);
+                        uint32_t nid[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const uint32_t pos = p0 + j * 32 + lane;
+                            // owner = the last lane whose list starts at or before pos (empty lists share their successor's start)
+                            uint32_t own = 0;
+#pragma unroll
+                            for (int step = 16; step > 0; step >>= 1) {
+                                const uint32_t st = __shfl_sync(kFull, start, own + step);
+                                if (st <= pos) own += step;
+                            }
+                            const uint64_t ob = __shfl_sync(kFull, b2, own);
+                            const uint32_t os = __shfl_sync(kFull, start, own);
+                            nid[j] = pos < total ? __ldg(p.csr_nbrs + ob + (pos - os)) : 0u;
+                        }
+                        uint32_t n = filter_unvisited_ids(w, tags, (uint8_t)epoch, nid, cnt, 0, 0xffffffffu);
+                        if (nqn > 1 && n > 1) n = dedupe_fresh(w, n);  // the same base row in two lists of this batch
+                        cmps += n;
+                        if (n) evaluate<kL2>(w, p, n, false);
+                    }
                 }
             }
         }

@@ -23,15 +23,36 @@ for mode in modes:
     for metric in ("ip",):
         rg.knn_dev(base[:4096], train[:256], K, metric, ids[:256], d[:256])  # warm-up (module load, attributes)
         torch.cuda.synchronize()
+        best = None
+        for rep in range(2):  # the first full-size call also grows the workspace
+            t0 = time.perf_counter()
+            rg.knn_dev(base, train, K, metric, ids, d)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        prof = rg.knn_profile() if os.environ.get("RG_KNN_TRACE") else None
+        # resident base (rg_knn_base_*): preparation once, then the query batch alone
         t0 = time.perf_counter()
-        rg.knn_dev(base, train, K, metric, ids, d)
+        kb = rg.KnnBase(base, metric)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        prep = time.perf_counter() - t0
+        sb = None
+        for rep in range(2):
+            t0 = time.perf_counter()
+            kb.search_dev(train, K, ids, d)
+            torch.cuda.synchronize()
+            dt2 = time.perf_counter() - t0
+            sb = dt2 if sb is None else min(sb, dt2)
+        kb.close()
+        dt = best
         res[mode] = ids.clone()
         tf = 2.0 * nq * nb * dim / dt / 1e12
         print(json.dumps({"mode": mode, "metric": metric, "nb": nb, "nq": nq, "dim": dim, "K": K, "seconds": dt,
                           "pairs_per_s": nq * nb / dt, "tflops": tf,
-                          "frac_of_measured_bf16_sustained": tf / peaks["bf16_tflops_sustained"]}), flush=True)
+                          "frac_of_measured_bf16_sustained": tf / peaks["bf16_tflops_sustained"],
+                          "resident_base": {"prepare_s": prep, "search_s": sb, "tflops": 2.0 * nq * nb * dim / sb / 1e12,
+                                            "frac_of_measured_bf16_sustained": 2.0 * nq * nb * dim / sb / 1e12 / peaks["bf16_tflops_sustained"]},
+                          "seed": os.environ.get("RG_KNN_SEED", "1"), "phases_ms_of_last_call": prof}), flush=True)
 if len(res) == 2:
     a, b = res["tc"], res["simt"]
     print(json.dumps({"ids_equal_fraction": float((a == b).float().mean())}))
