@@ -156,6 +156,15 @@ int rg_knn_release_workspace(void);
 int rg_topk_merge_dev(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
                       float *d_out_dists, uint32_t *d_out_ids, void *stream);
 
+/* The same merge for ONE all-gather per exchange (BASELINE.json north_star): rg_topk_pack_dev packs a shard's (distance, id)
+ * block into one 8-byte word per entry — high word = the float's bits, low word = id + id_offset (the shard's first global
+ * row, compute_groundtruth.cpp:413; the "no result" id 0xffffffff is kept) — and rg_topk_merge_packed_dev merges the
+ * gathered [G][nq][K_in] words into the K_out best per query for the queries [q_lo, q_hi) of the batch (out arrays are
+ * indexed by the query's position in the batch).  K_in may differ from K_out (a shard may return fewer than k). */
+int rg_topk_pack_dev(const float *d_dists, const uint32_t *d_ids, uint64_t n, uint32_t id_offset, uint64_t *d_packed, void *stream);
+int rg_topk_merge_packed_dev(const uint64_t *d_packed, uint32_t G, uint64_t nq, uint32_t K_in, uint32_t K_out, uint64_t q_lo,
+                             uint64_t q_hi, float *d_out_dists, uint32_t *d_out_ids, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

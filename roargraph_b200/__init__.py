@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
         L.rg_knn.argtypes = [vp, u64, vp, u64, u32, u32, C.c_int, i32, vp, vp]
         L.rg_knn_dev.argtypes = [vp, u64, vp, u64, u32, u32, C.c_int, i32, vp, vp, vp]
         L.rg_topk_merge_dev.argtypes = [vp, vp, u32, u64, u32, vp, vp, vp]
+        L.rg_topk_pack_dev.argtypes = [vp, vp, u64, u32, vp, vp]
+        L.rg_topk_merge_packed_dev.argtypes = [vp, u32, u64, u32, u32, u64, u64, vp, vp, vp]
         L.rg_knn_base_create.argtypes = [C.POINTER(vp), vp, u64, u32, C.c_int, C.c_int]
         L.rg_knn_base_destroy.argtypes = [vp]
         L.rg_knn_base_search_dev.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp]
@@ -338,3 +340,18 @@ def topk_merge_dev(d_in_dists, d_in_ids, d_out_dists, d_out_ids, stream=None) ->
     _check(lib().rg_topk_merge_dev(C.c_void_p(d_in_dists.data_ptr()), C.c_void_p(d_in_ids.data_ptr()), G, nq, K,
                                    C.c_void_p(d_out_dists.data_ptr()), C.c_void_p(d_out_ids.data_ptr()),
                                    _stream_ptr(stream)))
+
+
+def topk_pack_dev(d_dists, d_ids, id_offset: int, d_packed, stream=None) -> None:
+    """(dist, id)[...] -> one int64 word per entry (high = float bits, low = id + id_offset; 0xffffffff kept)."""
+    _check(lib().rg_topk_pack_dev(C.c_void_p(d_dists.data_ptr()), C.c_void_p(d_ids.data_ptr()), d_dists.numel(), id_offset,
+                                  C.c_void_p(d_packed.data_ptr()), _stream_ptr(stream)))
+
+
+def topk_merge_packed_dev(d_packed, d_out_dists, d_out_ids, q_lo: int = 0, q_hi: int | None = None, stream=None) -> None:
+    """[G, nq, K_in] packed words (an all-gather result) -> the K_out best per query into out[q_lo:q_hi]; out: [nq, K_out]."""
+    G, nq, K_in = d_packed.shape
+    K_out = d_out_dists.shape[1]
+    _check(lib().rg_topk_merge_packed_dev(C.c_void_p(d_packed.data_ptr()), G, nq, K_in, K_out, q_lo,
+                                          nq if q_hi is None else q_hi, C.c_void_p(d_out_dists.data_ptr()),
+                                          C.c_void_p(d_out_ids.data_ptr()), _stream_ptr(stream)))

@@ -702,4 +702,18 @@ int rg_topk_merge_dev(const float *d_in_dists, const uint32_t *d_in_ids, uint32_
     return topk_merge_device(d_in_dists, d_in_ids, G, nq, K, d_out_dists, d_out_ids, (cudaStream_t)stream);
 }
 
+int rg_topk_pack_dev(const float *d_dists, const uint32_t *d_ids, uint64_t n, uint32_t id_offset, uint64_t *d_packed, void *stream) {
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    return topk_pack_device(d_dists, d_ids, n, id_offset, reinterpret_cast<unsigned long long *>(d_packed), (cudaStream_t)stream);
+}
+
+int rg_topk_merge_packed_dev(const uint64_t *d_packed, uint32_t G, uint64_t nq, uint32_t K_in, uint32_t K_out, uint64_t q_lo,
+                             uint64_t q_hi, float *d_out_dists, uint32_t *d_out_ids, void *stream) {
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    return topk_merge_packed_device(reinterpret_cast<const unsigned long long *>(d_packed), G, nq, K_in, K_out, q_lo, q_hi,
+                                    d_out_dists, d_out_ids, (cudaStream_t)stream);
+}
+
 }  // extern "C"

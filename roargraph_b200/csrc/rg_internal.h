@@ -171,6 +171,10 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
 void knn_base_free(rg_knn_base *kb);
 // new object over device rows `d_base` (own_in: a device copy the object frees, or nullptr)
 int knn_base_new(rg_knn_base **out, const float *d_base, float *own_in, uint64_t nb, uint32_t dim, int metric);
+int topk_pack_device(const float *d_dists, const uint32_t *d_ids, uint64_t n, uint32_t id_offset, unsigned long long *d_packed,
+                     cudaStream_t s);
+int topk_merge_packed_device(const unsigned long long *d_packed, uint32_t G, uint64_t nq, uint32_t K_in, uint32_t K_out,
+                             uint64_t q_lo, uint64_t q_hi, float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s);
 int topk_merge_device(const float *d_in_dists, const uint32_t *d_in_ids, uint32_t G, uint64_t nq, uint32_t K,
                       float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s);
 

@@ -397,6 +397,50 @@ __global__ void topk_merge_kernel(const float *in_d, const uint32_t *in_i, uint3
     }
 }
 
+// (distance, id) pairs packed into one 8-byte word per entry so that a shard's whole top-K block travels in ONE all-gather:
+// high word = the distance's float bits, low word = the id, made global by the shard's first row (start_id,
+// compute_groundtruth.cpp:413); the "no result" sentinel 0xffffffff stays what it is.
+__global__ void topk_pack_kernel(const float *d, const uint32_t *id, uint64_t n, uint32_t id_offset, unsigned long long *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = id[i];
+    out[i] = ((unsigned long long)__float_as_uint(d[i]) << 32) | (v == 0xffffffffu ? v : v + id_offset);
+}
+
+// merge of G packed lists of K_in entries per query (each ascending in (distance, id)) into the K_out best, for the queries
+// [q_lo, q_hi) of a batch of nq: one warp per query, lane g owns the head of list g; entries with the sentinel id sort last
+__global__ void topk_merge_packed_kernel(const unsigned long long *in, uint32_t G, uint64_t nq, uint32_t K_in, uint32_t K_out,
+                                         uint64_t q_lo, uint64_t q_hi, float *out_d, uint32_t *out_i) {
+    const uint64_t q = q_lo + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= q_hi) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t head = 0;
+    const bool own = (uint32_t)lane < G;
+    const unsigned long long *l = in + ((uint64_t)lane * nq + q) * K_in;
+    for (uint32_t o = 0; o < K_out; ++o) {
+        unsigned long long key = ~0ull, raw = 0;
+        if (own && head < K_in) {
+            raw = l[head];
+            if ((uint32_t)raw != 0xffffffffu) key = ((unsigned long long)f2ord(__uint_as_float((uint32_t)(raw >> 32))) << 32) | (uint32_t)raw;
+        }
+        unsigned long long best = key;
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, s);
+            best = other < best ? other : best;
+        }
+        const uint32_t winners = best == ~0ull ? 0u : __ballot_sync(0xffffffffu, key == best);
+        if (winners && lane == __ffs(winners) - 1) {  // keys embed the global id: equal keys are the same entry seen twice
+            out_d[q * K_out + o] = __uint_as_float((uint32_t)(raw >> 32));
+            out_i[q * K_out + o] = (uint32_t)raw;
+            head++;
+        } else if (!winners && lane == 0) {
+            out_d[q * K_out + o] = INFINITY;
+            out_i[q * K_out + o] = 0xffffffffu;
+        }
+        __syncwarp();
+    }
+}
+
 // Scratch buffers of the kNN calls live in a grow-only per-device workspace: cudaMalloc / cudaFree of the multi-GB
 // candidate lists and the bf16 base copy cost ~10 % of a one-batch call, and a 10 M-query run re-enters with the same
 // sizes.  rg_knn_release_workspace() (knn_release_workspace) gives the memory of the current device back.
@@ -751,6 +795,27 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
 }
 
 void knn_reset_profile() { t_profile = KnnProfile{}; }
+
+int topk_pack_device(const float *d_dists, const uint32_t *d_ids, uint64_t n, uint32_t id_offset, unsigned long long *d_packed,
+                     cudaStream_t s) {
+    if (!d_dists || !d_ids || !d_packed) { set_error("rg_topk_pack: null buffer"); return RG_EINVAL; }
+    if (n == 0) return RG_OK;
+    topk_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_dists, d_ids, n, id_offset, d_packed);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
+int topk_merge_packed_device(const unsigned long long *d_packed, uint32_t G, uint64_t nq, uint32_t K_in, uint32_t K_out,
+                             uint64_t q_lo, uint64_t q_hi, float *d_out_dists, uint32_t *d_out_ids, cudaStream_t s) {
+    if (!d_packed || !d_out_dists || !d_out_ids) { set_error("rg_topk_merge_packed: null buffer"); return RG_EINVAL; }
+    if (G == 0 || G > 32) { set_error("rg_topk_merge_packed: G must be in [1, 32]"); return RG_EINVAL; }
+    if (K_in == 0 || K_out == 0 || q_hi > nq || q_lo > q_hi) { set_error("rg_topk_merge_packed: bad K / query range"); return RG_EINVAL; }
+    if (q_hi == q_lo) return RG_OK;
+    topk_merge_packed_kernel<<<(unsigned)((q_hi - q_lo + 3) / 4), 128, 0, s>>>(d_packed, G, nq, K_in, K_out, q_lo, q_hi, d_out_dists,
+                                                                             d_out_ids);
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
 
 void knn_release_workspace() {
     if (Workspace *ws = current_ws()) ws->release();

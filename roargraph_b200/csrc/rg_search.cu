@@ -468,26 +468,29 @@ __device__ __forceinline__ uint32_t filter_unvisited_ids(WarpCtx &w, uint8_t *ta
     __syncwarp();
     return ncand;
 }
-// cand[0..n) -> its distinct ids, first occurrences kept in order; returns their number.  The visited filter above reads all
-// tags of a 96-id batch before it writes any, so an id that occurs twice inside one batch passes twice; adjacency rows are
-// duplicate-free by construction (deduplicated at upload), the concatenated second-hop lists of the bipartite search are not.
-__device__ __forceinline__ uint32_t dedupe_fresh(WarpCtx &w, uint32_t n) {
+// cand[lo..hi) -> its distinct ids, first occurrences kept in order, compacted behind cand[lo); returns the new end.  The
+// visited filter above reads all tags of a 96-id batch before it writes any, so an id that occurs twice inside one batch
+// passes twice; adjacency rows are duplicate-free by construction (deduplicated at upload), the concatenated second-hop
+// lists of the bipartite search are not.  (Entries of EARLIER batches were tagged before this batch's tags were read.)
+__device__ __forceinline__ uint32_t dedupe_fresh(WarpCtx &w, uint32_t lo, uint32_t hi) {
     const int lane = w.lane;
+    const uint32_t n = hi - lo;
+    const uint32_t *c = w.cand + lo;
     uint32_t id[3];
     bool keep[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const uint32_t i = r * 32 + lane;
         keep[r] = i < n;
-        id[r] = keep[r] ? w.cand[i] : 0u;
+        id[r] = keep[r] ? c[i] : 0u;
         const uint32_t lim = min(n, (uint32_t)(r * 32 + 31));  // entries before the last lane of this row
-        for (uint32_t j = 0; j < lim; ++j) {                    // every lane reads cand[j]: a broadcast
-            const uint32_t c = w.cand[j];
-            if (j < i && c == id[r]) keep[r] = false;
+        for (uint32_t j = 0; j < lim; ++j) {                    // every lane reads c[j]: a broadcast
+            const uint32_t v = c[j];
+            if (j < i && v == id[r]) keep[r] = false;
         }
     }
     __syncwarp();  // every read precedes the compaction writes
-    uint32_t m = 0;
+    uint32_t m = lo;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const uint32_t b = __ballot_sync(kFull, keep[r]);
@@ -785,6 +788,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 // visited filter + dedupe_fresh here).  hops++ precedes the empty-adjacency skip (:320-323).
                 const uint64_t b = __ldg(p.row_off + u), e = __ldg(p.row_off + u + 1);
                 adjw += (uint32_t)(e - b);
+                uint32_t ncand = 0;  // fresh ids waiting in cand[]: evaluated once at least 64 have gathered (whole row groups)
                 for (uint64_t c0 = b; c0 < e; c0 += 32) {
                     const uint32_t nqn = (uint32_t)min((uint64_t)32, e - c0);
                     uint64_t b2 = 0;
@@ -803,9 +807,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                     const uint32_t start = incl - len;
                     const uint32_t total = __shfl_sync(kFull, incl, 31);
                     adjw += total;
-                    for (uint32_t p0 = 0; p0 < total; p0 += kCandCap) {
-                        const uint32_t cnt = min(total - p0, (uint32_t)kCandCap);
-                        uint32_t nid[3];
+                    // ids of flat positions p0 + [0, 96), three per lane
+                    auto load_ids = [&](uint32_t p0, uint32_t (&nid)[3]) {
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
                             const uint32_t pos = p0 + j * 32 + lane;
@@ -820,11 +823,27 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                             const uint32_t os = __shfl_sync(kFull, start, own);
                             nid[j] = pos < total ? __ldg(p.csr_nbrs + ob + (pos - os)) : 0u;
                         }
-                        uint32_t n = filter_unvisited_ids(w, tags, (uint8_t)epoch, nid, cnt, 0, 0xffffffffu);
-                        if (nqn > 1 && n > 1) n = dedupe_fresh(w, n);  // the same base row in two lists of this batch
-                        cmps += n;
-                        if (n) evaluate<kL2>(w, p, n, false);
+                    };
+                    uint32_t cur[3], nxt[3] = {0u, 0u, 0u};
+                    if (total) load_ids(0, cur);
+                    for (uint32_t p0 = 0; p0 < total; p0 += kCandCap) {
+                        if (p0 + kCandCap < total) load_ids(p0 + kCandCap, nxt);  // in flight while this batch is filtered / evaluated
+                        const uint32_t cnt = min(total - p0, (uint32_t)kCandCap);
+                        uint32_t n = filter_unvisited_ids(w, tags, (uint8_t)epoch, cur, cnt, ncand, 0xffffffffu);
+                        if (nqn > 1 && n > ncand + 1) n = dedupe_fresh(w, ncand, n);  // the same base row in two lists of this batch
+                        ncand = n;
+                        if (ncand >= 64u) {  // cand[] holds 2 x kCandCap ids in this mode
+                            cmps += ncand;
+                            evaluate<kL2>(w, p, ncand, false);
+                            ncand = 0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) cur[j] = nxt[j];
                     }
+                }
+                if (ncand) {
+                    cmps += ncand;
+                    evaluate<kL2>(w, p, ncand, false);
                 }
             }
         }
@@ -897,8 +916,8 @@ uint32_t env_u32(const char *name, uint32_t dflt) {
 
 constexpr uint32_t kMaxSmemPerCta = 227u * 1024u;
 
-uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L, uint32_t vt_bytes = 0) {
-    uint32_t b = 64 + dim * 4 + R * rstride * 4 + L * 8 + kCandCap * 4;
+uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L, uint32_t vt_bytes = 0, uint32_t cand_words = kCandCap) {
+    uint32_t b = 64 + dim * 4 + R * rstride * 4 + L * 8 + cand_words * 4;
     if (vt_bytes) b += 32 + vt_bytes;  // the shared-memory visited table, 32-byte aligned behind the candidate ids
     return (b + 127u) & ~127u;
 }
@@ -974,6 +993,9 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     p.row_stride_smem = dim + ((16u + 32u - (dim & 31u)) & 31u);  // stride % 32 == 16 -> conflict-free float4 reads
     const uint32_t env_warps = env_u32("RG_WARPS_PER_CTA", 0);
     const uint32_t vt_bytes = p.vt_smem ? p.vt_words * 4u : 0u;
+    // candidate-id scratch per warp: one 96-id pass; the bipartite search (row_off set) gathers the fresh ids of several
+    // passes before it evaluates them, so that whole 8-row groups go through the row ring
+    const uint32_t cw = p.row_off ? 2u * (uint32_t)kCandCap : (uint32_t)kCandCap;
     uint32_t warps = 4, ctas = 0;
     uint32_t R = env_u32("RG_ROWS_PER_BATCH", 0);
     if (R == 0) {
@@ -982,17 +1004,17 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
         // (profiles/r1_sweep_10M_ring.csv) it pays when the single-buffered geometry already saturates the memory system
         // (>= 20 warps per SM) or when it keeps at least 72 % of the resident warps.
         uint32_t w8c, c8, w16c, c16;
-        const uint32_t w8 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 8, p.L, vt_bytes), env_warps, w8c, c8);
-        const uint32_t w16 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 16, p.L, vt_bytes), env_warps, w16c, c16);
+        const uint32_t w8 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 8, p.L, vt_bytes, cw), env_warps, w8c, c8);
+        const uint32_t w16 = resident_geometry(warp_smem_bytes(dim, p.row_stride_smem, 16, p.L, vt_bytes, cw), env_warps, w16c, c16);
         R = (w16 > 0 && (w8 >= 20 || w16 * 100u >= w8 * 72u)) ? 16u : 8u;
     }
     if (R < 8) R = 8;
     if (R > (uint32_t)kMaxRowsPerBatch) R = kMaxRowsPerBatch;
     R &= ~7u;
-    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L, vt_bytes);
+    uint32_t wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L, vt_bytes, cw);
     while (wb > kMaxSmemPerCta && R > 8) {
         R -= 8;
-        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L, vt_bytes);
+        wb = warp_smem_bytes(dim, p.row_stride_smem, R, p.L, vt_bytes, cw);
     }
     if (wb > kMaxSmemPerCta) {
         set_error("L_pq / dim too large for one warp's shared-memory working set");

@@ -288,11 +288,11 @@ def test_build_bipartite_cli_then_search_bipartite_cli(tmp_path, golden):
         assert c.returncode == 0, c.stdout + c.stderr
         tc = _bipartite_table(c.stdout)
         R = Reference(detrand=True)
-        queries = F.pad_rows(golden.test_raw)
+        queries = F.pad_rows(F.read_fbin(qf))  # the fixture's queries tiled to >= 100 rows (_write_case)
         if golden.metric == "cosine":
             queries = R.normalize_rows(queries)
         h = R.bipartite_load(bf, bp, golden.metric, queries.shape[1], golden.z["train_knn_ids"].shape[0], 2)
-        gt = golden.z["gt_ids"]
+        gt, _ = F.read_truthset(gf)
         for L in Ls:
             r = R.search_bipartite(h, queries, 5, L, 2, seed_base=seed)
             hit = sum(int((r["ids"] == gt[:, j:j + 1]).any(axis=1).sum()) for j in range(5))

@@ -84,16 +84,22 @@ def _knn_worker(rank, world, port, out):
         ids.copy_(torch.from_numpy(i.astype(np.int32) + id_offset))
         dists.copy_(torch.from_numpy(d))
 
-    def merge(all_d, all_i, out_d, out_i):  # (distance asc, id asc), as rg_topk_merge_dev
-        G, n, k = all_d.shape
-        d = all_d.numpy().transpose(1, 0, 2).reshape(n, G * k)
-        i = all_i.numpy().transpose(1, 0, 2).reshape(n, G * k)
-        order = np.lexsort((i, d), axis=1)[:, :k]
-        out_d.copy_(torch.from_numpy(np.take_along_axis(d, order, 1)))
-        out_i.copy_(torch.from_numpy(np.take_along_axis(i, order, 1)))
-
     ids, dists = sharded_knn_dev(torch.from_numpy(g.base_raw[lo:hi]), torch.from_numpy(g.test_raw), K, "l2", lo, batch=17,
-                                 local_knn=local_knn, merge=merge)
+                                 local_knn=local_knn)
+    # slice_only: every rank merges only its share of each 17-query batch; the union over the ranks is the full answer
+    si, sd = sharded_knn_dev(torch.from_numpy(g.base_raw[lo:hi]), torch.from_numpy(g.test_raw), K, "l2", lo, batch=17,
+                             local_knn=local_knn, slice_only=True)
+    nq = g.test_raw.shape[0]
+    mine = np.zeros(nq, dtype=bool)
+    for b0 in range(0, nq, 17):
+        n = min(17, nq - b0)
+        per = -(-n // world)
+        mine[b0 + min(rank * per, n):b0 + min((rank + 1) * per, n)] = True
+    assert torch.equal(si[torch.from_numpy(mine)], ids[torch.from_numpy(mine)])
+    assert torch.equal(sd[torch.from_numpy(mine)], dists[torch.from_numpy(mine)])
+    cover = torch.from_numpy(mine.astype(np.int32))
+    dist.all_reduce(cover)
+    assert bool((cover == 1).all())  # every query belongs to exactly one rank's slice
     if rank == 1:  # every rank holds the full answer
         np.savez(out, d=dists.numpy(), i=ids.numpy())
     dist.barrier()
@@ -185,3 +191,68 @@ def test_two_rank_query_sharded_knn(tmp_path, oracle, nq):
     g = GoldenCase("l2_d104")
     full_i, full_d = oracle.exact_knn(g.base_raw, g.test_raw[:nq], 9, "l2")
     assert (z["i"] == full_i).all() and (z["d"].view(np.uint32) == full_d.view(np.uint32)).all()
+
+
+def _sharded_search_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    from roargraph_b200 import RgError
+    from roargraph_b200.sharded import ShardedRoarIndex, raise_on_all_ranks
+    O = Oracle()
+    g = GoldenCase("ip_d40")
+    nb = g.base.shape[0]
+    lo, hi = shard_range(nb, rank, world)
+    nq = g.queries.shape[0]
+
+    def local_search(d_q, k, L, out_ids, out_dists):  # exact top-k of the slice stands in for the per-shard index search;
+        ids, dists = O.exact_knn(g.base[lo:hi], d_q.numpy(), k, "ip")  # rank 1 pretends query 3 found only 2 results
+        ids = ids.astype(np.int32)
+        if rank == 1:
+            ids[3, 2:] = -1
+            dists[3, 2:] = np.inf
+        out_ids.copy_(torch.from_numpy(ids))
+        out_dists.copy_(torch.from_numpy(dists))
+
+    sidx = ShardedRoarIndex(None, row_lo=lo, local_search=local_search)
+    res = {}
+    for ks in (10, 6):
+        ids = torch.empty((nq, 10), dtype=torch.int32)
+        dists = torch.empty((nq, 10), dtype=torch.float32)
+        assert sidx.search_dev(torch.from_numpy(g.queries), 10, 32, ids, dists, k_shard=ks) == 3
+        res[ks] = (ids.numpy().copy(), dists.numpy().copy())
+    if rank == 0:
+        np.savez(out, i10=res[10][0], d10=res[10][1], i6=res[6][0], d6=res[6][1])
+    # a failure on one rank raises on every rank instead of leaving the peers in the next collective
+    err = RgError(-3, "not enough results: 2, expected: 10") if rank == 1 else None
+    try:
+        raise_on_all_ranks(err, torch.device("cpu"))
+        raised = False
+    except RgError:
+        raised = True
+    assert raised
+    raise_on_all_ranks(None, torch.device("cpu"))  # and nothing happens when every rank is fine
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_search_packed_exchange(tmp_path, oracle):
+    """ShardedRoarIndex over gloo: ONE packed all-gather, global ids, the short-result sentinel is neither offset nor
+    merged in front of real results, k_shard < k keeps the k best of 2 x k_shard, errors surface on every rank."""
+    out = str(tmp_path / "sharded.npz")
+    mp.spawn(_sharded_search_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    z = np.load(out)
+    g = GoldenCase("ip_d40")
+    nb = g.base.shape[0]
+    full_i, full_d = oracle.exact_knn(g.base, g.queries, 10, "ip")
+    keep = np.ones(len(full_i), dtype=bool)
+    keep[3] = False  # the query rank 1 truncated
+    np.testing.assert_allclose(z["d10"][keep], full_d[keep], rtol=1e-6, atol=1e-6)
+    assert (z["i10"][keep] == full_i[keep]).mean() > 0.999
+    assert (z["i10"] != -1).all() and (z["i10"] >= 0).all() and (z["i10"] < nb).all()  # 2 x 10 entries: the sentinel never surfaces
+    assert np.isfinite(z["d10"]).all() and (np.diff(z["d10"], axis=1) >= 0).all()
+    # k_shard = 6: the 10 best of 2 x 6; equal to the exact answer wherever neither shard holds more than 6 of the top-10
+    lo1 = nb // 2
+    share = (full_i < lo1).sum(1)
+    ok = keep & (share <= 6) & (share >= 4)
+    assert ok.sum() > 10 and (z["i6"][ok] == full_i[ok]).mean() > 0.999
