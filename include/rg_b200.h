@@ -145,6 +145,8 @@ int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq,
  * out[0..6] = base preparation, query conversion, tau seed pass, tensor-core filter, re-rank/merge, chunks, overflow retries. */
 int rg_knn_profile(double *out7);
 int rg_knn_profile_reset(void);
+/* on = 1 / 0: switch the per-phase timers on / off for this process whatever RG_KNN_TRACE says; -1: follow the environment. */
+int rg_knn_trace(int on);
 
 /* rg_knn / rg_knn_dev keep their device scratch (bf16 operand copies, candidate lists; a few GB at 10 M rows) in a
  * grow-only per-process workspace so that repeated calls do not pay cudaMalloc/cudaFree; this gives it back. */

@@ -329,6 +329,11 @@ def knn_profile(reset: bool = False) -> dict:
     return {k: float(v) for k, v in zip(keys, out)}
 
 
+def knn_trace(on: int) -> None:
+    """1 / 0: per-phase timers of the kNN calls on / off (a diagnostic pass: they synchronise); -1: follow RG_KNN_TRACE."""
+    _check(lib().rg_knn_trace(int(on)))
+
+
 def knn_release_workspace() -> None:
     """Free the device scratch rg_knn / rg_knn_dev keep between calls."""
     _check(lib().rg_knn_release_workspace())

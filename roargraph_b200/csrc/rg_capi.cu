@@ -690,6 +690,11 @@ int rg_knn_profile_reset(void) {
     return RG_OK;
 }
 
+int rg_knn_trace(int on) {
+    knn_set_trace(on);
+    return RG_OK;
+}
+
 int rg_knn_release_workspace(void) {
     knn_release_workspace();
     return RG_OK;

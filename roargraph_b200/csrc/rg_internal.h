@@ -156,6 +156,7 @@ struct KnnProfile {
 };
 const KnnProfile &knn_last_profile();
 void knn_reset_profile();
+void knn_set_trace(int on);
 
 // BuildRoarGraph (rg_build.cu)
 int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, uint32_t knn_stride, uint32_t M_sq,

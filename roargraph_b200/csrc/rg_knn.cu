@@ -486,13 +486,14 @@ Workspace *current_ws() {
     } while (0)
 
 // RG_KNN_TRACE=1: device time of every phase (events + a stream synchronisation per phase: a diagnostic, never the timed path)
+int g_trace_override = -1;  // rg_knn_trace(): 1 / 0 force the per-phase timers on / off, -1 = follow RG_KNN_TRACE
 struct PhaseTimer {
     bool on;
     cudaStream_t s;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     PhaseTimer(cudaStream_t st) : s(st) {
         static const bool env = getenv("RG_KNN_TRACE") != nullptr;
-        on = env;
+        on = g_trace_override < 0 ? env : g_trace_override != 0;
         if (on) {
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
@@ -795,6 +796,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
 }
 
 void knn_reset_profile() { t_profile = KnnProfile{}; }
+void knn_set_trace(int on) { g_trace_override = on; }
 
 int topk_pack_device(const float *d_dists, const uint32_t *d_ids, uint64_t n, uint32_t id_offset, unsigned long long *d_packed,
                      cudaStream_t s) {

@@ -30,33 +30,60 @@ def make_numpy(nb: int, nq_train: int, nq_test: int, dim: int, seed: int = 1234,
     return base.astype(np.float32), train, test
 
 
-def make_torch(nb: int, nq_train: int, nq_test: int, dim: int, device, seed: int = 1234, latent: int = 64,
-               chunk: int = 1 << 20):
-    """Same distribution family generated on `device` with torch's generator (not bit-identical to make_numpy)."""
-    import torch
+class TorchSynth:
+    """The generator's parameters on `device` (same distribution family as make_numpy, torch's generator): base rows once,
+    then any number of query sets from the SAME modality-gap distribution — training queries, test queries, and the
+    10 M-query batch stream of BASELINE.json configs[3]."""
 
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    nclus = max(16, nb // 1000)
-    rn = lambda *s: torch.randn(*s, generator=gen, device=device, dtype=torch.float32)
-    A = rn(latent, dim) / latent ** 0.5
-    cent = rn(nclus, latent)
-    base = torch.empty(nb, dim, device=device, dtype=torch.float32)
-    for s in range(0, nb, chunk):
-        e = min(nb, s + chunk)
-        c = torch.randint(0, nclus, (e - s,), generator=gen, device=device)
-        base[s:e] = (cent[c] + rn(e - s, latent)) @ A + 0.3 * rn(e - s, dim)
-    g = 0.5 * rn(dim)
-    B = A + 0.15 * rn(latent, dim) / latent ** 0.5
+    def __init__(self, nb: int, dim: int, device, seed: int = 1234, latent: int = 64, chunk: int = 1 << 20):
+        import torch
 
-    def queries(n):
-        out = torch.empty(n, dim, device=device, dtype=torch.float32)
-        for s in range(0, n, chunk):
-            e = min(n, s + chunk)
-            c = torch.randint(0, nclus, (e - s,), generator=gen, device=device)
-            out[s:e] = (cent[c] + 1.2 * rn(e - s, latent)) @ B + 0.3 * rn(e - s, dim) + g
+        self.nb, self.dim, self.device, self.latent, self.chunk = nb, dim, device, latent, chunk
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+        self.nclus = max(16, nb // 1000)
+        self.A = self._rn(latent, dim) / latent ** 0.5
+        self.cent = self._rn(self.nclus, latent)
+        self._have_base = False
+
+    def _rn(self, *s):
+        import torch
+        return torch.randn(*s, generator=self.gen, device=self.device, dtype=torch.float32)
+
+    def base(self):
+        import torch
+
+        assert not self._have_base, "the base is drawn once, before any query set (the generator is sequential)"
+        out = torch.empty(self.nb, self.dim, device=self.device, dtype=torch.float32)
+        for s in range(0, self.nb, self.chunk):
+            e = min(self.nb, s + self.chunk)
+            c = torch.randint(0, self.nclus, (e - s,), generator=self.gen, device=self.device)
+            out[s:e] = (self.cent[c] + self._rn(e - s, self.latent)) @ self.A + 0.3 * self._rn(e - s, self.dim)
+        self.g = 0.5 * self._rn(self.dim)
+        self.B = self.A + 0.15 * self._rn(self.latent, self.dim) / self.latent ** 0.5
+        self._have_base = True
         return out
 
-    train = queries(nq_train)
-    test = queries(nq_test)
+    def queries(self, n: int, out=None):
+        import torch
+
+        assert self._have_base
+        if out is None:
+            out = torch.empty(n, self.dim, device=self.device, dtype=torch.float32)
+        for s in range(0, n, self.chunk):
+            e = min(n, s + self.chunk)
+            c = torch.randint(0, self.nclus, (e - s,), generator=self.gen, device=self.device)
+            out[s:e] = (self.cent[c] + 1.2 * self._rn(e - s, self.latent)) @ self.B + 0.3 * self._rn(e - s, self.dim) + self.g
+        return out
+
+
+def make_torch(nb: int, nq_train: int, nq_test: int, dim: int, device, seed: int = 1234, latent: int = 64,
+               chunk: int = 1 << 20, return_gen: bool = False):
+    """Same distribution family generated on `device` with torch's generator (not bit-identical to make_numpy)."""
+    gen = TorchSynth(nb, dim, device, seed=seed, latent=latent, chunk=chunk)
+    base = gen.base()
+    train = gen.queries(nq_train)
+    test = gen.queries(nq_test)
+    if return_gen:
+        return base, train, test, gen
     return base, train, test

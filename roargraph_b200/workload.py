@@ -55,6 +55,23 @@ def recall_at_k(res_ids: np.ndarray, gt_ids: np.ndarray, k: int) -> float:
     return hit / float(k * res_ids.shape[0])
 
 
+def bipartite_csr(knn_ids: np.ndarray, nd: int, M_pjbp: int):
+    """Vectorised qbaseNNbipartite: query node nd + sq -> its first M_pjbp NNs except (every occurrence of) the top-1;
+    base node top-1(sq) -> nd + sq, in ascending sq (the reference's single-thread order)."""
+    nn = np.ascontiguousarray(knn_ids[:, :M_pjbp]).astype(np.uint32)
+    nsq = nn.shape[0]
+    tgt = nn[:, 0]
+    keep = nn != tgt[:, None]
+    q_deg = keep.sum(1)
+    order = np.argsort(tgt, kind="stable")
+    b_deg = np.bincount(tgt, minlength=nd)
+    row_off = np.zeros(nd + nsq + 1, dtype=np.uint64)
+    row_off[1:nd + 1] = np.cumsum(b_deg)
+    row_off[nd + 1:] = row_off[nd] + np.cumsum(q_deg).astype(np.uint64)
+    nbrs = np.concatenate([(order + nd).astype(np.uint32), nn[keep]])
+    return row_off, nbrs
+
+
 class SearchWorkload:
     """Device-resident shard of a synthetic cross-modal search problem + its RoarGraph index."""
 
@@ -69,7 +86,32 @@ class SearchWorkload:
         self.metric = "ip"
         self.k = 10
         self.d_train_sample = None # torch [<=151552, dim]: training queries kept for bench.py's brute-force kNN leg
+        self.gen = None            # synth.TorchSynth: more queries of the same distribution on demand (make_queries)
         self.info = {}
+
+    def make_queries(self, n: int):
+        """n more queries from the generator's query distribution, treated like the test queries (padded to x8, normalised
+        for cosine).  Deterministic given the seed and the call sequence, so every rank of a job draws the same rows."""
+        q = _pad8(self.gen.queries(n))
+        if self.metric == "cosine":
+            _normalize_rows_(q)
+        return q
+
+    def exact_topk(self, d_q, k: int):
+        """Exact top-k (global ids, uint32 numpy) of device-resident queries over the FULL base: the local brute-force kNN
+        on one rank, the base-sharded kNN (all-gather + merge) when this workload is one shard of several."""
+        import torch
+        from roargraph_b200.sharded import ShardedKnn
+
+        knn_metric = "l2" if self.metric == "l2" else "ip"
+        sk = ShardedKnn(self.d_base, knn_metric, self.row_lo)
+        try:
+            ids, _ = sk.search(d_q, k)
+            torch.cuda.synchronize(d_q.device)
+            return ids.cpu().numpy().view(np.uint32)
+        finally:
+            sk.close()
+            rg.knn_release_workspace()
 
 
 def _cache_key(**kw) -> str:
@@ -89,7 +131,7 @@ def build_search_workload(nb: int, dim: int, metric: str, ntrain: int, nq: int, 
     w = SearchWorkload()
     w.metric, w.k, w.nd_total = metric, k, nb
     t0 = time.time()
-    base, train, test = synth.make_torch(nb, ntrain, nq, dim, dev, seed=seed)
+    base, train, test, w.gen = synth.make_torch(nb, ntrain, nq, dim, dev, seed=seed, return_gen=True)
     base, train, test = _pad8(base), _pad8(train), _pad8(test)
     if metric == "cosine":  # the reference normalises base rows at load and queries in the CLI
         _normalize_rows_(base)

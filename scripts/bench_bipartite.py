@@ -18,23 +18,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def bipartite_csr(knn_ids: np.ndarray, nd: int, M_pjbp: int):
-    """Vectorised qbaseNNbipartite: query node nd + sq -> its first M_pjbp NNs except (every occurrence of) the top-1;
-    base node top-1(sq) -> nd + sq, in ascending sq (the reference's single-thread order)."""
-    nn = np.ascontiguousarray(knn_ids[:, :M_pjbp]).astype(np.uint32)
-    nsq = nn.shape[0]
-    tgt = nn[:, 0]
-    keep = nn != tgt[:, None]
-    q_deg = keep.sum(1)
-    order = np.argsort(tgt, kind="stable")
-    b_deg = np.bincount(tgt, minlength=nd)
-    row_off = np.zeros(nd + nsq + 1, dtype=np.uint64)
-    row_off[1:nd + 1] = np.cumsum(b_deg)
-    row_off[nd + 1:] = row_off[nd] + np.cumsum(q_deg).astype(np.uint64)
-    nbrs = np.concatenate([(order + nd).astype(np.uint32), nn[keep]])
-    return row_off, nbrs
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nb", type=int, default=10_000_000)
@@ -48,7 +31,7 @@ def main():
 
     import roargraph_b200 as rg
     from roargraph_b200 import synth
-    from roargraph_b200.workload import recall_at_k, log
+    from roargraph_b200.workload import bipartite_csr, recall_at_k, log
 
     rg.init(0)
     dev = torch.device("cuda", 0)
