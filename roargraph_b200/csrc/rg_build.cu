@@ -305,16 +305,25 @@ __global__ void seg_offsets_kernel(const unsigned long long *keys, uint64_t n, u
     off[d] = lo;
 }
 
-// CalculateProjectionep (:2004-2041): centroid, then the row closest to it in squared L2 (lowest id on ties)
-__global__ void colsum_kernel(const float *base, uint64_t nd, uint32_t dim, double *sum) {
-    const uint32_t d = threadIdx.x;
+// CalculateProjectionep (:2004-2041): centroid, then the row closest to it in squared L2 (lowest id on ties).  The column
+// sums are formed in double precision in a FIXED order (per-block partial sums over a contiguous row range, then the
+// partials summed in block order), so the centroid — and with it the entry point — does not depend on scheduling; the
+// reference adds the rows one after the other in fp32, which differs from the exact sum by more than this does.
+__global__ void colsum_partial_kernel(const float *base, uint64_t nd, uint32_t dim, double *partial) {
     const uint64_t rows_per = (nd + gridDim.x - 1) / gridDim.x;
     const uint64_t r0 = (uint64_t)blockIdx.x * rows_per, r1 = min(nd, r0 + rows_per);
-    for (uint32_t dd = d; dd < dim; dd += blockDim.x) {
+    for (uint32_t dd = threadIdx.x; dd < dim; dd += blockDim.x) {
         double s = 0.0;
         for (uint64_t r = r0; r < r1; ++r) s += (double)base[r * dim + dd];
-        atomicAdd(sum + dd, s);
+        partial[(uint64_t)blockIdx.x * dim + dd] = s;
     }
+}
+__global__ void colsum_final_kernel(const double *partial, uint32_t n_partial, uint32_t dim, double *sum) {
+    const uint32_t dd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dd >= dim) return;
+    double s = 0.0;
+    for (uint32_t b = 0; b < n_partial; ++b) s += partial[(uint64_t)b * dim + dd];
+    sum[dd] = s;
 }
 __global__ void closest_to_center_kernel(const float *base, uint64_t nd, uint32_t dim, const double *sum,
                                          unsigned long long *best) {
@@ -454,9 +463,15 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
     RG_CUDA(cudaMemsetAsync(supply, 0, (size_t)nd * sstride * 4, s));
 
     // entry point
-    RG_CUDA(cudaMemsetAsync(b_sum.p, 0, dim * 8, s));
     RG_CUDA(cudaMemsetAsync(b_best.p, 0xff, 8, s));
-    colsum_kernel<<<std::min<uint32_t>(nd, 4096), 256, 0, s>>>(idx->d_base, nd, dim, b_sum.as<double>());
+    {
+        const uint32_t n_partial = std::min<uint32_t>(nd, 4096);
+        Buf b_partial;
+        if ((rc = b_partial.alloc((size_t)n_partial * dim * 8))) return rc;
+        colsum_partial_kernel<<<n_partial, 256, 0, s>>>(idx->d_base, nd, dim, b_partial.as<double>());
+        colsum_final_kernel<<<(dim + 255) / 256, 256, 0, s>>>(b_partial.as<double>(), n_partial, dim, b_sum.as<double>());
+        RG_CUDA(cudaStreamSynchronize(s));  // b_partial goes out of scope
+    }
     closest_to_center_kernel<<<(nd + 7) / 8, 256, 0, s>>>(idx->d_base, nd, dim, b_sum.as<double>(), b_best.as<unsigned long long>());
     unsigned long long h_best = 0;
     RG_CUDA(cudaMemcpyAsync(&h_best, b_best.p, 8, cudaMemcpyDeviceToHost, s));

@@ -89,3 +89,64 @@ def test_build_statistically_matches_reference_build():
         assert r_gpu > r_ref - 0.03, (L, r_ref, r_gpu)
     ref_idx.close()
     idx.close()
+
+
+def test_build_at_1M_against_the_reference_build_statistics():
+    """BASELINE configs[0] size: 1 M x 200 IP, README build parameters.  tests/golden/ref_build_1M_stats.json holds what the
+    reference's own BuildRoarGraph + SearchRoarGraph produced on the same seeded data on the build container's cores
+    (scripts/ref_build_fixture.py: entry point, degree histogram, recall / cmps over the README L_pq sweep).  The device
+    build must pick the same entry point (CalculateProjectionep, src/index_bipartite.cpp:2004-2041), stay within 10 % of the
+    reference's mean degree, and reach the reference's recall at every L_pq of the sweep to within 0.01 (not below it)."""
+    import json
+    import torch
+    from conftest import GOLDEN
+    from roargraph_b200.workload import README_L_SWEEP
+    ref = json.load(open(os.path.join(GOLDEN, "ref_build_1M_stats.json")))
+    nb, dim = ref["nb"], ref["dim"]
+    base, train, test = synth.make_numpy(nb, ref["ntrain"], ref["nq"], dim, seed=ref["seed"])
+    d_base = torch.from_numpy(F.pad_rows(base)).cuda()
+    d_train = torch.from_numpy(F.pad_rows(train)).cuda()
+    d_test = torch.from_numpy(F.pad_rows(test)).cuda()
+    kn_i = torch.empty((ref["ntrain"], 100), dtype=torch.int32, device="cuda")
+    kn_d = torch.empty((ref["ntrain"], 100), dtype=torch.float32, device="cuda")
+    rg.knn_dev(d_base, d_train, 100, "ip", kn_i, kn_d)
+    gt_i = torch.empty((ref["nq"], 10), dtype=torch.int32, device="cuda")
+    gt_d = torch.empty((ref["nq"], 10), dtype=torch.float32, device="cuda")
+    rg.knn_dev(d_base, d_test, 10, "ip", gt_i, gt_d)
+    torch.cuda.synchronize()
+    gt = gt_i.cpu().numpy().view(np.uint32)
+    idx = rg.RoarIndex(d_base, "ip")
+    idx.build_roargraph(kn_i, ref["M_sq"], ref["M_pjbp"], ref["L_pjpq"])
+    g = idx.graph_size()
+    assert g["ep"] == ref["ep"], (g["ep"], ref["ep"])
+    avg = g["nnz"] / nb
+    assert abs(avg - ref["avg_degree"]) / ref["avg_degree"] < 0.10, (avg, ref["avg_degree"])
+    assert g["max_degree"] <= 2 * ref["M_pjbp"]
+    ep, row_off, _ = idx.get_graph()
+    deg = np.diff(row_off.astype(np.int64))
+    hist = np.bincount(deg, minlength=len(ref["degree_hist"]))[:len(ref["degree_hist"])] / nb
+    ref_hist = np.array(ref["degree_hist"], dtype=np.float64) / nb
+    tv = 0.5 * np.abs(hist - ref_hist).sum()  # total-variation distance of the two degree distributions
+    d_i = torch.empty((ref["nq"], 10), dtype=torch.int32, device="cuda")
+    d_d = torch.empty((ref["nq"], 10), dtype=torch.float32, device="cuda")
+    d_c = torch.empty(ref["nq"], dtype=torch.int32, device="cuda")
+    rows, worst = [], 0.0
+    by_L = {r["L_pq"]: r for r in ref["sweep"]}
+    for L in README_L_SWEEP:
+        idx.search_dev(d_test, 10, L, d_i, d_d, d_c, None)
+        idx.check()
+        rec = recall_at_k(d_i.cpu().numpy().view(np.uint32), gt, 10)
+        cm = float(d_c.float().mean().item())
+        rows.append((L, rec, by_L[L]["recall"], cm, by_L[L]["avg_cmps"]))
+        worst = max(worst, by_L[L]["recall"] - rec)
+    out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    if os.path.isdir(out):  # evidence for profiles/: the two curves side by side
+        with open(os.path.join(out, "build_1M_vs_reference.csv"), "w") as f:
+            f.write(f"# device build: avg degree {avg:.3f} max {g['max_degree']} ep {g['ep']}; reference build: avg degree "
+                    f"{ref['avg_degree']:.3f} max {ref['max_degree']} ep {ref['ep']}; degree-distribution TV distance {tv:.4f}\n")
+            f.write("L_pq,recall_device_build,recall_reference_build,avg_cmps_device_build,avg_cmps_reference_build\n")
+            for r in rows:
+                f.write(",".join(f"{x:.6g}" for x in r) + "\n")
+    assert worst <= 0.01, (worst, [r for r in rows if r[2] - r[1] > 0.01])
+    assert tv < 0.25, tv
+    idx.close()
