@@ -167,6 +167,40 @@ int rg_topk_pack_dev(const float *d_dists, const uint32_t *d_ids, uint64_t n, ui
 int rg_topk_merge_packed_dev(const uint64_t *d_packed, uint32_t G, uint64_t nq, uint32_t K_in, uint32_t K_out, uint64_t q_lo,
                              uint64_t q_hi, float *d_out_dists, uint32_t *d_out_ids, void *stream);
 
+/* ---- several GPUs of one box from ONE host process ------------------------------------------------------------------
+ * The reference's CLIs are single processes; for BASELINE.json's multi-GPU configurations the drop-in stays one process
+ * and gives every GPU one worker thread and one NCCL rank (ncclCommInitAll; libnccl.so.2 is bound at run time, only when a
+ * group of more than one GPU is created).  The base rows are sharded by equal counts like compute_groundtruth's base parts
+ * (compute_groundtruth.cpp:396-416): shard s = rows [s*nd/G, (s+1)*nd/G) on GPU dev_ids[s] (NULL = 0..n_gpus-1), ids made
+ * global by the shard's first row (:413), per exchange step ONE all-gather of the packed per-shard top-k blocks and the
+ * k-way merge (:424-444).  Python / torchrun jobs use one process per GPU and torch.distributed for the same exchange
+ * (roargraph_b200/sharded.py). */
+typedef struct rg_group rg_group;
+typedef struct rg_sharded_index rg_sharded_index;
+int rg_group_create(rg_group **out, int n_gpus, const int *dev_ids);
+int rg_group_destroy(rg_group *g);
+int rg_group_size(rg_group *g);
+/* exact_knn with the base sharded over the group (BASELINE configs[3]); host buffers, contract of rg_knn: every GPU keeps
+ * its base part prepared, uploads 1/G of each 151 552-query batch (the rows are all-gathered over NVLink), scores the
+ * batch against its part, and merges + returns its 1/G slice of the batch's queries after the packed all-gather. */
+int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queries, uint64_t nq, uint32_t dim, uint32_t K,
+                 int metric, int32_t *ids, float *dists);
+/* Base-sharded RoarGraph search (BASELINE configs[4]): one rg_index per shard, each with its OWN graph over its rows.
+ * base: host rows, padded like rg_index_create's.  rg_sharded_index_shard hands out shard s's rg_index (e.g. for
+ * rg_index_set_graph with LOCAL ids, rg_index_get_graph, rg_search_last_stats) and its first global row / row count.
+ * rg_sharded_index_build_roargraph computes every shard's own learn-base kNN lists (the training queries against the
+ * shard's rows, K = M_sq) and builds its graph on its GPU.  rg_sharded_search_roargraph: host buffers; every GPU uploads 1/G
+ * of the batch, NVLink all-gather of the rows, per-shard SearchRoarGraph at L_pq, packed all-gather, merge; ids are global
+ * rows, (distance asc, id asc) — the merge of the reference's per-shard results. */
+int rg_sharded_index_create(rg_group *g, rg_sharded_index **out, const float *base, uint64_t nd, uint32_t dim, int metric);
+int rg_sharded_index_destroy(rg_sharded_index *si);
+int rg_sharded_index_shards(rg_sharded_index *si);
+int rg_sharded_index_shard(rg_sharded_index *si, int shard, rg_index **index, uint64_t *row_lo, uint64_t *rows);
+int rg_sharded_index_build_roargraph(rg_sharded_index *si, const float *train, uint64_t nsq, uint32_t M_sq, uint32_t M_pjbp,
+                                     uint32_t L_pjpq);
+int rg_sharded_search_roargraph(rg_sharded_index *si, const float *queries, uint32_t nq, uint32_t k, uint32_t L_pq, uint32_t *ids,
+                                float *dists);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,16 @@ def lib() -> C.CDLL:
         L.rg_topk_merge_dev.argtypes = [vp, vp, u32, u64, u32, vp, vp, vp]
         L.rg_topk_pack_dev.argtypes = [vp, vp, u64, u32, vp, vp]
         L.rg_topk_merge_packed_dev.argtypes = [vp, u32, u64, u32, u32, u64, u64, vp, vp, vp]
+        L.rg_group_create.argtypes = [C.POINTER(vp), C.c_int, vp]
+        L.rg_group_destroy.argtypes = [vp]
+        L.rg_group_size.argtypes = [vp]
+        L.rg_group_knn.argtypes = [vp, vp, u64, vp, u64, u32, u32, C.c_int, vp, vp]
+        L.rg_sharded_index_create.argtypes = [vp, C.POINTER(vp), vp, u64, u32, C.c_int]
+        L.rg_sharded_index_destroy.argtypes = [vp]
+        L.rg_sharded_index_shards.argtypes = [vp]
+        L.rg_sharded_index_shard.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+        L.rg_sharded_index_build_roargraph.argtypes = [vp, vp, u64, u32, u32, u32]
+        L.rg_sharded_search_roargraph.argtypes = [vp, vp, u32, u32, u32, vp, vp]
         L.rg_knn_base_create.argtypes = [C.POINTER(vp), vp, u64, u32, C.c_int, C.c_int]
         L.rg_knn_base_destroy.argtypes = [vp]
         L.rg_knn_base_search_dev.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp]
@@ -135,9 +145,18 @@ class RoarIndex:
             self.nd, self.dim = base.shape
             _check(lib().rg_index_create(C.byref(self._h), C.c_void_p(base.data_ptr()), self.nd, self.dim, m, 1))
 
+    @classmethod
+    def _borrowed(cls, handle, nd: int, dim: int, metric: int) -> "RoarIndex":
+        """A view of an rg_index owned by someone else (a shard of a GroupShardedIndex): close() does not destroy it."""
+        self = cls.__new__(cls)
+        self._h, self._keep, self._owned = C.c_void_p(handle), None, False
+        self.nd, self.dim, self.metric = nd, dim, metric
+        return self
+
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
-            lib().rg_index_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().rg_index_destroy(self._h)
             self._h = C.c_void_p(0)
 
     def __del__(self):
@@ -360,3 +379,77 @@ def topk_merge_packed_dev(d_packed, d_out_dists, d_out_ids, q_lo: int = 0, q_hi:
     _check(lib().rg_topk_merge_packed_dev(C.c_void_p(d_packed.data_ptr()), G, nq, K_in, K_out, q_lo,
                                           nq if q_hi is None else q_hi, C.c_void_p(d_out_dists.data_ptr()),
                                           C.c_void_p(d_out_ids.data_ptr()), _stream_ptr(stream)))
+
+
+class Group:
+    """Several GPUs of one box driven from THIS process (rg_group_*: one worker thread and one NCCL rank per GPU) — the
+    single-process form the C++ CLIs use for BASELINE.json's multi-GPU configurations."""
+
+    def __init__(self, n_gpus: int, dev_ids=None):
+        self._h = C.c_void_p(0)
+        arr = (C.c_int * n_gpus)(*dev_ids) if dev_ids is not None else None
+        _check(lib().rg_group_create(C.byref(self._h), n_gpus, arr))
+        self.n = n_gpus
+
+    def knn(self, base: np.ndarray, queries: np.ndarray, K: int, metric: str | int):
+        """exact_knn with the base sharded over the group's GPUs: -> ids[nq,K] int32, dists[nq,K] float32."""
+        m = METRIC[metric] if isinstance(metric, str) else int(metric)
+        b = np.ascontiguousarray(base, dtype=np.float32)
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        ids = np.empty((q.shape[0], K), dtype=np.int32)
+        dists = np.empty((q.shape[0], K), dtype=np.float32)
+        _check(lib().rg_group_knn(self._h, _np_ptr(b), b.shape[0], _np_ptr(q), q.shape[0], b.shape[1], K, m, _np_ptr(ids),
+                                  _np_ptr(dists)))
+        return ids, dists
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rg_group_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupShardedIndex:
+    """Base rows sharded over the GPUs of a Group, one RoarGraph per shard (rg_sharded_index_*)."""
+
+    def __init__(self, group: Group, base: np.ndarray, metric: str | int):
+        self._h = C.c_void_p(0)
+        self.group = group
+        m = METRIC[metric] if isinstance(metric, str) else int(metric)
+        self.metric = m
+        b = np.ascontiguousarray(base, dtype=np.float32)
+        self.nd, self.dim = b.shape
+        _check(lib().rg_sharded_index_create(group._h, C.byref(self._h), _np_ptr(b), self.nd, self.dim, m))
+
+    def shard(self, s: int):
+        """-> (RoarIndex view of shard s, first global row, rows)"""
+        h, lo, n = C.c_void_p(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().rg_sharded_index_shard(self._h, s, C.byref(h), C.byref(lo), C.byref(n)))
+        return RoarIndex._borrowed(h.value, n.value, self.dim, self.metric), lo.value, n.value
+
+    def build_roargraph(self, train: np.ndarray, M_sq: int = 100, M_pjbp: int = 35, L_pjpq: int = 500) -> None:
+        t = np.ascontiguousarray(train, dtype=np.float32)
+        _check(lib().rg_sharded_index_build_roargraph(self._h, _np_ptr(t), t.shape[0], M_sq, M_pjbp, L_pjpq))
+
+    def search(self, queries: np.ndarray, k: int, L_pq: int):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        ids = np.empty((q.shape[0], k), dtype=np.uint32)
+        dists = np.empty((q.shape[0], k), dtype=np.float32)
+        _check(lib().rg_sharded_search_roargraph(self._h, _np_ptr(q), q.shape[0], k, L_pq, _np_ptr(ids), _np_ptr(dists)))
+        return ids, dists
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().rg_sharded_index_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cstdlib>
@@ -270,12 +271,10 @@ int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, cons
 int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_off, const uint32_t *nbrs) {
     if (!idx || !row_off || n_total < idx->nd) { set_error("rg_index_set_bipartite: bad argument"); return RG_EINVAL; }
     { int rc_dev_ = enter_index(idx); if (rc_dev_ != RG_OK) return rc_dev_; }
-    // dedupe each list (same argument as in rg_index_set_graph) while rebuilding the CSR
-    std::vector<uint64_t> ro(n_total + 1, 0);
-    std::vector<uint32_t> out;
-    out.reserve(row_off[n_total]);
+    const uint64_t nd = idx->nd;
+    if (!nbrs && row_off[n_total] != 0) { set_error("rg_index_set_bipartite: null neighbour array"); return RG_EINVAL; }
     for (uint64_t u = 0; u < n_total; ++u) {
-        const size_t start = out.size();
+        if (row_off[u + 1] < row_off[u]) { set_error("rg_index_set_bipartite: row_off not monotone"); return RG_EINVAL; }
         for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
             const uint32_t v = nbrs[j];
             if (v >= n_total) { set_error("rg_index_set_bipartite: neighbour id out of range"); return RG_EINVAL; }
@@ -283,20 +282,77 @@ int rg_index_set_bipartite(rg_index *idx, uint64_t n_total, const uint64_t *row_
             // search evaluates against the base array and tags in a visited array of nd entries (:326-334); a base node
             // points at query nodes, whose lists are walked as second hops.  A base -> base edge would make a base id a
             // "query node" and its neighbours' neighbours — possibly query-node ids >= nd — rows of the base array.
-            if (u >= idx->nd && v >= idx->nd) { set_error("rg_index_set_bipartite: query node points at a query node"); return RG_EINVAL; }
-            if (u < idx->nd && v < idx->nd) { set_error("rg_index_set_bipartite: base node points at a base node"); return RG_EINVAL; }
-            if (std::find(out.begin() + start, out.end(), v) == out.end()) out.push_back(v);
+            if (u >= nd && v >= nd) { set_error("rg_index_set_bipartite: query node points at a query node"); return RG_EINVAL; }
+            if (u < nd && v < nd) { set_error("rg_index_set_bipartite: base node points at a base node"); return RG_EINVAL; }
         }
-        ro[u + 1] = out.size();
     }
-    if (idx->d_row_off) cudaFree(idx->d_row_off);
-    if (idx->d_csr) cudaFree(idx->d_csr);
-    idx->d_row_off = nullptr;
-    idx->d_csr = nullptr;
-    RG_CUDA(cudaMalloc(&idx->d_row_off, ro.size() * sizeof(uint64_t)));
-    RG_CUDA(cudaMalloc(&idx->d_csr, std::max<size_t>(out.size(), 1) * sizeof(uint32_t)));
-    RG_CUDA(cudaMemcpy(idx->d_row_off, ro.data(), ro.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    if (!out.empty()) RG_CUDA(cudaMemcpy(idx->d_csr, out.data(), out.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // Device layout: the search only ever walks base node -> query node -> base node (:324-341), so every base node u gets
+    // ONE contiguous list: the distinct base ids reachable through its query nodes, in first-occurrence order.  An id that
+    // sits in several of u's second-hop lists is evaluated once by the reference too (its visited array) and the order
+    // inside a hop is unobservable, so cmps, hops and results are unchanged — while the kernel reads one
+    // coalesced id list per hop instead of chasing row_off / ids per query node, and probes every visited tag once.
+    std::vector<uint64_t> ro(nd + 1, 0);
+    {
+        // pass 1 (parallel over base nodes): distinct two-hop ids per node, counted
+        const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        std::vector<std::vector<uint32_t>> chunk_ids(nt);
+        std::vector<std::vector<uint32_t>> chunk_cnt(nt);
+        std::vector<std::thread> th;
+        const uint64_t per = (nd + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t]() {
+                const uint64_t u0 = std::min<uint64_t>((uint64_t)t * per, nd), u1 = std::min<uint64_t>(u0 + per, nd);
+                std::vector<uint32_t> &out = chunk_ids[t];
+                std::vector<uint32_t> &cnt = chunk_cnt[t];
+                cnt.assign(u1 - u0, 0);
+                std::vector<uint32_t> seen;  // open-addressing set of the current node's ids
+                for (uint64_t u = u0; u < u1; ++u) {
+                    uint64_t raw = 0;
+                    for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) raw += row_off[nbrs[j] + 1] - row_off[nbrs[j]];
+                    if (!raw) continue;
+                    uint64_t cap = 16;
+                    while (cap < 2 * raw) cap <<= 1;
+                    seen.assign(cap, 0xffffffffu);
+                    const size_t start = out.size();
+                    for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
+                        const uint32_t qn = nbrs[j];
+                        for (uint64_t i = row_off[qn]; i < row_off[qn + 1]; ++i) {
+                            const uint32_t v = nbrs[i];
+                            uint64_t h = ((uint64_t)v * 0x9E3779B97F4A7C15ull >> 20) & (cap - 1);
+                            while (seen[h] != 0xffffffffu && seen[h] != v) h = (h + 1) & (cap - 1);
+                            if (seen[h] == v) continue;
+                            seen[h] = v;
+                            out.push_back(v);
+                        }
+                    }
+                    cnt[u - u0] = (uint32_t)(out.size() - start);
+                }
+            });
+        for (auto &x : th) x.join();
+        // pass 2: offsets + concatenation in node order
+        uint64_t total = 0;
+        for (unsigned t = 0; t < nt; ++t) {
+            const uint64_t u0 = std::min<uint64_t>((uint64_t)t * per, nd);
+            for (size_t i = 0; i < chunk_cnt[t].size(); ++i) {
+                ro[u0 + i] = total;
+                total += chunk_cnt[t][i];
+            }
+        }
+        ro[nd] = total;
+        if (idx->d_row_off) cudaFree(idx->d_row_off);
+        if (idx->d_csr) cudaFree(idx->d_csr);
+        idx->d_row_off = nullptr;
+        idx->d_csr = nullptr;
+        RG_CUDA(cudaMalloc(&idx->d_row_off, ro.size() * sizeof(uint64_t)));
+        RG_CUDA(cudaMalloc(&idx->d_csr, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+        RG_CUDA(cudaMemcpy(idx->d_row_off, ro.data(), ro.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        uint64_t at = 0;
+        for (unsigned t = 0; t < nt; ++t) {
+            if (chunk_ids[t].empty()) continue;
+            RG_CUDA(cudaMemcpy(idx->d_csr + at, chunk_ids[t].data(), chunk_ids[t].size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            at += chunk_ids[t].size();
+        }
+    }
     idx->n_total = n_total;
     idx->has_bipartite = true;
     return RG_OK;

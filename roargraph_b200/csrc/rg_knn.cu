@@ -128,6 +128,7 @@ struct Rerank {
     const float *qn, *bn;         // squared norms (L2)
     uint32_t dim;
     int metric_l2;
+    int vec;  // rows are 16-byte aligned with dim % 4 == 0: float4 loads (and that accumulation order) in both merge kernels
 };
 
 // A query's candidate list is `cap` words; the 2-CTA tensor-core filter fills it as two private sub-lists (one per
@@ -177,12 +178,14 @@ __device__ void merge_query_big(uint64_t q, unsigned long long *__restrict__ top
     if (n == 0) return;
     unsigned long long *cq = cand + q * cap;
     if (rr.base) {
-        float *sq = reinterpret_cast<float *>(sk + sort_n);  // dim floats after the sort buffer
+        float *sq = reinterpret_cast<float *>(sk + sort_n);  // dim floats after the sort buffer (16-byte aligned: sort_n * 8)
         for (uint32_t j = threadIdx.x; j < rr.dim; j += blockDim.x) sq[j] = rr.queries[q * rr.dim + j];
         __syncthreads();
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         const float qq = rr.metric_l2 ? rr.qn[q] : 0.f;
-        // four candidates per warp pass: their row loads are independent, so the DRAM latencies overlap
+        // four candidates per warp pass: their row loads are independent, so the DRAM latencies overlap.  Every candidate's
+        // partial sums are formed in exactly the order of knn_merge_fast_kernel (lane-strided float4 groups x, y, z, w when
+        // `vec`, lane-strided scalars otherwise; xor-shuffle tree), so a distance does not depend on which kernel re-ranked it
         for (uint32_t i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
             uint32_t b[4];
             const float *br[4];
@@ -192,10 +195,24 @@ __device__ void merge_query_big(uint64_t q, unsigned long long *__restrict__ top
                 b[t] = (uint32_t)cq[cl.slot(min(i0 + t, n - 1))];
                 br[t] = rr.base + (uint64_t)b[t] * rr.dim;
             }
-            for (uint32_t j = lane; j < rr.dim; j += 32) {
-                const float qv = sq[j];
+            if (rr.vec) {
+                for (uint32_t j = lane; j < rr.dim / 4; j += 32) {
+                    const float4 qv = reinterpret_cast<const float4 *>(sq)[j];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) acc[t] = fmaf(qv, __ldg(br[t] + j), acc[t]);
+                    for (int t = 0; t < 4; ++t) {
+                        const float4 x = __ldg(reinterpret_cast<const float4 *>(br[t]) + j);
+                        acc[t] = fmaf(qv.x, x.x, acc[t]);
+                        acc[t] = fmaf(qv.y, x.y, acc[t]);
+                        acc[t] = fmaf(qv.z, x.z, acc[t]);
+                        acc[t] = fmaf(qv.w, x.w, acc[t]);
+                    }
+                }
+            } else {
+                for (uint32_t j = lane; j < rr.dim; j += 32) {
+                    const float qv = sq[j];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fmaf(qv, __ldg(br[t] + j), acc[t]);
+                }
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t)
@@ -705,6 +722,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
     if (fast_sn > sort_n) fast_sn = sort_n;
     const size_t fast_smem = (size_t)fast_sn * 8 + (size_t)dim * 4;
     const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(kb->B) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
+    rr.vec = vec ? 1 : 0;
     RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
     RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
     uint32_t *work_cnt = worklist + qb_alloc;

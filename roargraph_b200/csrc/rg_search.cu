@@ -468,39 +468,6 @@ __device__ __forceinline__ uint32_t filter_unvisited_ids(WarpCtx &w, uint8_t *ta
     __syncwarp();
     return ncand;
 }
-// cand[lo..hi) -> its distinct ids, first occurrences kept in order, compacted behind cand[lo); returns the new end.  The
-// visited filter above reads all tags of a 96-id batch before it writes any, so an id that occurs twice inside one batch
-// passes twice; adjacency rows are duplicate-free by construction (deduplicated at upload), the concatenated second-hop
-// lists of the bipartite search are not.  (Entries of EARLIER batches were tagged before this batch's tags were read.)
-__device__ __forceinline__ uint32_t dedupe_fresh(WarpCtx &w, uint32_t lo, uint32_t hi) {
-    const int lane = w.lane;
-    const uint32_t n = hi - lo;
-    const uint32_t *c = w.cand + lo;
-    uint32_t id[3];
-    bool keep[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const uint32_t i = r * 32 + lane;
-        keep[r] = i < n;
-        id[r] = keep[r] ? c[i] : 0u;
-        const uint32_t lim = min(n, (uint32_t)(r * 32 + 31));  // entries before the last lane of this row
-        for (uint32_t j = 0; j < lim; ++j) {                    // every lane reads c[j]: a broadcast
-            const uint32_t v = c[j];
-            if (j < i && v == id[r]) keep[r] = false;
-        }
-    }
-    __syncwarp();  // every read precedes the compaction writes
-    uint32_t m = lo;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const uint32_t b = __ballot_sync(kFull, keep[r]);
-        if (keep[r]) w.cand[m + __popc(b & ((1u << lane) - 1u))] = id[r];
-        m += __popc(b);
-    }
-    __syncwarp();
-    return m;
-}
-
 // ---- visited table --------------------------------------------------------------------------------------------------------
 // Exact visited set of one query in 2^bbits buckets of 16 x 16-bit entries (one 32-byte sector per bucket).  With
 // h = (id * mul) mod 2^bits (a bijection, mul odd) the bucket is the top bbits of h and the entry stores the low rbits
@@ -779,67 +746,36 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                     }
                 }
             } else {
-                // Two-hop expansion through the query nodes (:324-341), flattened: the current node's query-node list is read
-                // cooperatively (one id per lane), every lane fetches the CSR bounds of its query node in ONE round trip, and the
-                // concatenation of the second-hop lists streams through the visited filter 96 ids at a time exactly like a
-                // RoarGraph adjacency row — instead of one dependent row_off / id / tag / row chain per query node.  The
-                // reference walks the lists one after the other; the order inside a hop is unobservable, and an
-                // id that sits in several lists of the hop is evaluated once here as there (the visited array there, the
-                // visited filter + dedupe_fresh here).  hops++ precedes the empty-adjacency skip (:320-323).
+                // Two-hop expansion through the query nodes (:324-341): row_off / csr_nbrs hold, per BASE node, the distinct base
+                // ids reachable through its query nodes (rg_index_set_bipartite flattens base -> query -> base at upload; an id
+                // that sits in several second-hop lists of the node is evaluated once by the reference too, and the order
+                // inside a hop is unobservable).  The list streams through the visited filter 96 ids at a time
+                // like a RoarGraph adjacency row; the ids of the next pass are loaded before this pass is filtered, and fresh
+                // ids gather across passes so that whole 8-row groups go through the row ring.  hops++ precedes the
+                // empty-adjacency skip (:320-323).
                 const uint64_t b = __ldg(p.row_off + u), e = __ldg(p.row_off + u + 1);
                 adjw += (uint32_t)(e - b);
-                uint32_t ncand = 0;  // fresh ids waiting in cand[]: evaluated once at least 64 have gathered (whole row groups)
-                for (uint64_t c0 = b; c0 < e; c0 += 32) {
-                    const uint32_t nqn = (uint32_t)min((uint64_t)32, e - c0);
-                    uint64_t b2 = 0;
-                    uint32_t len = 0;
-                    if ((uint32_t)lane < nqn) {
-                        const uint32_t nbr = __ldg(p.csr_nbrs + c0 + lane);
-                        b2 = __ldg(p.row_off + nbr);
-                        len = (uint32_t)(__ldg(p.row_off + nbr + 1) - b2);
+                uint32_t ncand = 0;  // fresh ids waiting in cand[] (2 x kCandCap words in this mode)
+                auto load_ids = [&](uint64_t off, uint32_t (&nid)[3]) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint64_t pos = off + j * 32 + lane;
+                        nid[j] = pos < e ? __ldg(p.csr_nbrs + pos) : 0u;
                     }
-                    uint32_t incl = len;  // inclusive prefix sum of the list lengths over the lanes
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                        if (lane >= o) incl += t;
+                };
+                uint32_t cur[3], nxt[3] = {0u, 0u, 0u};
+                if (b < e) load_ids(b, cur);
+                for (uint64_t off = b; off < e; off += kCandCap) {
+                    if (off + kCandCap < e) load_ids(off + kCandCap, nxt);  // in flight while this pass is filtered / evaluated
+                    const uint32_t cnt = (uint32_t)min((uint64_t)kCandCap, e - off);
+                    ncand = filter_unvisited_ids(w, tags, (uint8_t)epoch, cur, cnt, ncand, 0xffffffffu);
+                    if (ncand >= 64u) {
+                        cmps += ncand;
+                        evaluate<kL2>(w, p, ncand, false);
+                        ncand = 0;
                     }
-                    const uint32_t start = incl - len;
-                    const uint32_t total = __shfl_sync(kFull, incl, 31);
-                    adjw += total;
-                    // ids of flat positions p0 + [0, 96), three per lane
-                    auto load_ids = [&](uint32_t p0, uint32_t (&nid)[3]) {
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            const uint32_t pos = p0 + j * 32 + lane;
-                            // owner = the last lane whose list starts at or before pos (empty lists share their successor's start)
-                            uint32_t own = 0;
-#pragma unroll
-                            for (int step = 16; step > 0; step >>= 1) {
-                                const uint32_t st = __shfl_sync(kFull, start, own + step);
-                                if (st <= pos) own += step;
-                            }
-                            const uint64_t ob = __shfl_sync(kFull, b2, own);
-                            const uint32_t os = __shfl_sync(kFull, start, own);
-                            nid[j] = pos < total ? __ldg(p.csr_nbrs + ob + (pos - os)) : 0u;
-                        }
-                    };
-                    uint32_t cur[3], nxt[3] = {0u, 0u, 0u};
-                    if (total) load_ids(0, cur);
-                    for (uint32_t p0 = 0; p0 < total; p0 += kCandCap) {
-                        if (p0 + kCandCap < total) load_ids(p0 + kCandCap, nxt);  // in flight while this batch is filtered / evaluated
-                        const uint32_t cnt = min(total - p0, (uint32_t)kCandCap);
-                        uint32_t n = filter_unvisited_ids(w, tags, (uint8_t)epoch, cur, cnt, ncand, 0xffffffffu);
-                        if (nqn > 1 && n > ncand + 1) n = dedupe_fresh(w, ncand, n);  // the same base row in two lists of this batch
-                        ncand = n;
-                        if (ncand >= 64u) {  // cand[] holds 2 x kCandCap ids in this mode
-                            cmps += ncand;
-                            evaluate<kL2>(w, p, ncand, false);
-                            ncand = 0;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) cur[j] = nxt[j];
-                    }
+                    for (int j = 0; j < 3; ++j) cur[j] = nxt[j];
                 }
                 if (ncand) {
                     cmps += ncand;

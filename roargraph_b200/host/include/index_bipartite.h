@@ -31,6 +31,8 @@
 #include "efanna2e/util.h"
 
 struct rg_index;
+struct rg_group;
+struct rg_sharded_index;
 
 namespace efanna2e {
 
@@ -51,6 +53,13 @@ class IndexBipartite : public Index {
   inline void LoadSearchNeededData(const char *base_file, const char *sampled_query_file) {
     LoadVectorData(base_file, sampled_query_file);
   }
+  // --gpus N of the CLIs (call before any data is loaded): the base rows are sharded over the first N GPUs of the box by
+  // equal counts (compute_groundtruth's base parts), every shard owns its OWN RoarGraph over its rows, and a search runs
+  // every query on every shard and merges the per-shard top-k after one all-gather (include/rg_b200.h, rg_sharded_*).
+  // Index files become one file per shard, "<path>.shard<s>of<N>", each a valid reference index over that shard's rows.
+  void SetGpus(uint32_t n);
+  uint32_t GetGpus() const { return gpus_; }
+  static std::string ShardFile(const std::string &path, uint32_t shard, uint32_t n_shards);
   // Hand over base rows already in host memory (stride == GetDimension(), normalised for COSINE); copied to HBM.
   void SetBaseData(const float *base, size_t n);
 
@@ -107,6 +116,9 @@ class IndexBipartite : public Index {
   float *owned_base_ = nullptr;
   size_t dev_dim_ = 0;  // row stride on the device when it differs from GetDimension() (unpadded build input)
   rg_index *dev_ = nullptr;
+  uint32_t gpus_ = 1;
+  rg_group *group_ = nullptr;
+  rg_sharded_index *sharded_ = nullptr;
   std::mutex call_mutex_;  // one caller at a time per rg_index
 };
 

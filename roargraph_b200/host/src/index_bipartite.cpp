@@ -55,7 +55,19 @@ IndexBipartite::IndexBipartite(const size_t dimension, const size_t n, Metric m,
 
 IndexBipartite::~IndexBipartite() {
   if (dev_) rg_index_destroy(dev_);
+  if (sharded_) rg_sharded_index_destroy(sharded_);
+  if (group_) rg_group_destroy(group_);
   free(owned_base_);
+}
+
+void IndexBipartite::SetGpus(uint32_t n) {
+  if (n == 0) throw std::invalid_argument("--gpus must be at least 1");
+  if (dev_ || sharded_) throw std::runtime_error("SetGpus must be called before data is loaded");
+  gpus_ = n;
+}
+
+std::string IndexBipartite::ShardFile(const std::string &path, uint32_t shard, uint32_t n_shards) {
+  return path + ".shard" + std::to_string(shard) + "of" + std::to_string(n_shards);
 }
 
 void IndexBipartite::Fail(int rc) const {
@@ -65,8 +77,15 @@ void IndexBipartite::Fail(int rc) const {
 }
 
 void IndexBipartite::EnsureDeviceIndex() {
-  if (dev_) return;
+  if (dev_ || sharded_) return;
   if (!data_bp_) throw std::runtime_error("base data not loaded");
+  if (gpus_ > 1) {
+    int rc = rg_group_create(&group_, (int)gpus_, nullptr);
+    if (rc != RG_OK) Fail(rc);
+    rc = rg_sharded_index_create(group_, &sharded_, data_bp_, nd_, (uint32_t)(dev_dim_ ? dev_dim_ : dimension_), to_rg_metric(metric_));
+    if (rc != RG_OK) Fail(rc);
+    return;
+  }
   int rc = rg_index_create(&dev_, data_bp_, nd_, (uint32_t)(dev_dim_ ? dev_dim_ : dimension_), to_rg_metric(metric_), 0);
   if (rc != RG_OK) Fail(rc);
 }
@@ -75,6 +94,10 @@ void IndexBipartite::SetBaseData(const float *base, size_t n) {
   if (dev_) {
     rg_index_destroy(dev_);
     dev_ = nullptr;
+  }
+  if (sharded_) {
+    rg_sharded_index_destroy(sharded_);
+    sharded_ = nullptr;
   }
   data_bp_ = base;
   nd_ = n;
@@ -118,6 +141,33 @@ void IndexBipartite::UploadProjectionGraph() {
 }
 
 void IndexBipartite::LoadProjectionGraph(const char *filename) {
+  if (gpus_ > 1) {  // one index file per shard, local ids
+    EnsureDeviceIndex();
+    for (uint32_t s = 0; s < gpus_; ++s) {
+      const std::string f = ShardFile(filename, s, gpus_);
+      std::ifstream in(f, std::ios::binary);
+      if (!in.is_open()) throw std::runtime_error("cannot open index file " + f);
+      uint32_t ep = 0, npts = 0;
+      in.read((char *)&ep, 4);
+      in.read((char *)&npts, 4);
+      CompactGraph g;
+      double deg = 0;
+      read_adjacency(in, npts, g, deg);
+      rg_index *shard = nullptr;
+      uint64_t lo = 0, rows = 0;
+      int rc = rg_sharded_index_shard(sharded_, (int)s, &shard, &lo, &rows);
+      if (rc != RG_OK) Fail(rc);
+      if (npts != rows) throw std::runtime_error("index file " + f + " does not match the shard's rows");
+      std::cout << "Projection graph shard " << s << " (rows " << lo << ".." << lo + rows << "), ep: " << ep
+                << ", avg_degree: " << deg / npts << std::endl;
+      std::vector<uint64_t> row_off;
+      std::vector<uint32_t> nbrs;
+      to_csr(g, row_off, nbrs);
+      rc = rg_index_set_graph(shard, ep, row_off.data(), nbrs.data());
+      if (rc != RG_OK) Fail(rc);
+    }
+    return;
+  }
   std::ifstream in(filename, std::ios::binary);
   if (!in.is_open()) throw std::runtime_error(std::string("cannot open index file ") + filename);
   uint32_t npts = 0;
@@ -151,6 +201,32 @@ IndexBipartite::CompactGraph &IndexBipartite::GetProjectionGraph() {
 }
 
 void IndexBipartite::SaveProjectionGraph(const char *filename) {
+  if (gpus_ > 1) {  // one file per shard in the reference's format (:2606-2619), local ids
+    if (!sharded_) throw std::runtime_error("index not built");
+    for (uint32_t s = 0; s < gpus_; ++s) {
+      rg_index *shard = nullptr;
+      uint64_t lo = 0, rows = 0, nnz = 0;
+      uint32_t ep = 0, md = 0;
+      int rc = rg_sharded_index_shard(sharded_, (int)s, &shard, &lo, &rows);
+      if (rc == RG_OK) rc = rg_index_graph_size(shard, &nnz, &ep, &md);
+      if (rc != RG_OK) Fail(rc);
+      std::vector<uint64_t> row_off(rows + 1);
+      std::vector<uint32_t> nbrs(nnz);
+      rc = rg_index_get_graph(shard, row_off.data(), nbrs.data());
+      if (rc != RG_OK) Fail(rc);
+      std::ofstream out(ShardFile(filename, s, gpus_), std::ios::binary | std::ios::out);
+      if (!out.is_open()) throw std::runtime_error("cannot open file");
+      const uint32_t npts = (uint32_t)rows;
+      out.write((const char *)&ep, 4);
+      out.write((const char *)&npts, 4);
+      for (uint64_t i = 0; i < rows; ++i) {
+        const uint32_t d = (uint32_t)(row_off[i + 1] - row_off[i]);
+        out.write((const char *)&d, 4);
+        out.write((const char *)(nbrs.data() + row_off[i]), (std::streamsize)d * 4);
+      }
+    }
+    return;
+  }
   CompactGraph &g = GetProjectionGraph();
   std::ofstream out(filename, std::ios::binary | std::ios::out);
   if (!out.is_open()) throw std::runtime_error("cannot open file");
@@ -287,7 +363,7 @@ void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_
   const uint32_t M_sq = parameters.Get<uint32_t>("M_sq");
   const uint32_t M_pjbp = parameters.Get<uint32_t>("M_pjbp");
   const uint32_t L_pjpq = parameters.Get<uint32_t>("L_pjpq");
-  if (learn_base_knn_.empty()) throw std::runtime_error("LoadLearnBaseKNN must be called before BuildRoarGraph");
+  if (learn_base_knn_.empty() && gpus_ == 1) throw std::runtime_error("LoadLearnBaseKNN must be called before BuildRoarGraph");
   if (need_normalize) {
     std::cout << "normalizing base data" << std::endl;
     normalize_rows(const_cast<float *>(bp_data), n_bp, dimension_);
@@ -306,6 +382,25 @@ void IndexBipartite::BuildRoarGraph(size_t n_sq, const float *sq_data, size_t n_
     bp_data = padded;
   }
   SetBaseData(bp_data, n_bp);
+  if (gpus_ > 1) {
+    // every shard needs the training queries' neighbours INSIDE the shard: they are computed on the shard's GPU from the
+    // training vectors (the learn-base kNN file holds the neighbours over the whole base, which is not what a shard needs)
+    if (!sq_data) throw std::runtime_error("the sharded build (--gpus > 1) needs the training-query vectors");
+    std::cout << "begin link projection on " << gpus_ << " shards" << std::endl;
+    int rc = rg_sharded_index_build_roargraph(sharded_, sq_data, n_sq, M_sq, M_pjbp, L_pjpq);
+    if (rc != RG_OK) Fail(rc);
+    for (uint32_t s = 0; s < gpus_; ++s) {
+      rg_index *shard = nullptr;
+      uint64_t lo = 0, rows = 0, nnz = 0;
+      uint32_t ep = 0, md = 0;
+      rg_sharded_index_shard(sharded_, (int)s, &shard, &lo, &rows);
+      rg_index_graph_size(shard, &nnz, &ep, &md);
+      std::cout << "shard " << s << ": projection ep: " << ep << ", Projection degree avg: " << (double)nnz / (double)rows
+                << ", Projection degree max: " << md << std::endl;
+    }
+    has_built = true;
+    return;
+  }
   const size_t nsq = learn_base_knn_.size();
   size_t stride = 0;
   for (auto &r : learn_base_knn_) stride = std::max(stride, r.size());
@@ -336,6 +431,13 @@ void IndexBipartite::SearchRoarGraphBatch(const float *queries, size_t nq, size_
   // an rg_index takes one caller at a time; the reference's CLIs call SearchRoarGraph from an OpenMP loop on one shared
   // index (tests/test_search_roargraph.cpp:203), so concurrent callers queue here
   std::lock_guard<std::mutex> guard(call_mutex_);
+  if (sharded_) {  // per-query cmps / hops are per-shard quantities: LastSearchStats sums them over the shards
+    int rc = rg_sharded_search_roargraph(sharded_, queries, (uint32_t)nq, (uint32_t)k, L_pq, indices, dists);
+    if (rc != RG_OK) Fail(rc);
+    if (cmps) std::fill(cmps, cmps + nq, 0u);
+    if (hops) std::fill(hops, hops + nq, 0u);
+    return;
+  }
   if (!dev_) throw std::runtime_error("index not loaded");
   int rc = rg_search_roargraph(dev_, queries, (uint32_t)nq, (uint32_t)k, L_pq, indices, dists, cmps, hops);
   if (rc != RG_OK) Fail(rc);
@@ -407,6 +509,19 @@ void IndexBipartite::Search(const float *query, const float *x, size_t k, const 
 
 void IndexBipartite::LastSearchStats(uint64_t &cmps, uint64_t &hops, uint64_t &adj_words) const {
   cmps = hops = adj_words = 0;
+  if (sharded_) {
+    for (uint32_t s = 0; s < gpus_; ++s) {
+      rg_index *shard = nullptr;
+      uint64_t c = 0, h = 0, a = 0;
+      if (rg_sharded_index_shard(sharded_, (int)s, &shard, nullptr, nullptr) == RG_OK &&
+          rg_search_last_stats(shard, &c, &h, &a) == RG_OK) {
+        cmps += c;
+        hops += h;
+        adj_words += a;
+      }
+    }
+    return;
+  }
   if (dev_) rg_search_last_stats(dev_, &cmps, &hops, &adj_words);
 }
 

@@ -4,6 +4,9 @@
 // (int32 n, int32 K, n*K uint32 ids, n*K float distances; +IP for mips, :438-439; squared L2 otherwise).
 // The base is processed in parts of at most PARTSIZE rows like the reference (:32, :396-448); each part is one
 // rg_knn call (ids offset by the part's first row, :413) and parts are merged per query by (distance, id).
+// --gpus N (the one added flag, default 1): every part is sharded over N GPUs of the box by rg_group_knn — the same part
+// loop one level down: every GPU keeps its rows prepared, the query batches stream past, ONE packed all-gather + merge per
+// batch (BASELINE.json configs[3]).
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
@@ -71,7 +74,12 @@ static uint64_t num_points(const std::string &path) {
 
 template <typename T>
 static int aux_main(const std::string &base_file, const std::string &query_file, const std::string &gt_file, uint64_t K,
-                    int metric) {
+                    int metric, int gpus) {
+  rg_group *group = nullptr;
+  if (gpus > 1) {
+    if (rg_group_create(&group, gpus, nullptr) != RG_OK) throw std::runtime_error(rg_last_error());
+    std::cout << "base parts sharded over " << gpus << " GPUs" << std::endl;
+  }
   std::vector<float> queries, base;
   uint64_t nq = 0, dim = 0, qd = 0, dummy = 0;
   load_bin_as_float<T>(query_file, queries, nq, qd, 0, dummy);
@@ -89,7 +97,14 @@ static int aux_main(const std::string &base_file, const std::string &query_file,
     std::vector<float> &od = p == 0 && parts == 1 ? dists : part_d;
     oi.assign(nq * Kp, -1);
     od.assign(nq * Kp, 0.f);
-    int rc = rg_knn(base.data(), np, queries.data(), nq, (uint32_t)dim, (uint32_t)Kp, metric, (int32_t)start, oi.data(), od.data());
+    int rc;
+    if (group) {
+      rc = rg_group_knn(group, base.data(), np, queries.data(), nq, (uint32_t)dim, (uint32_t)Kp, metric, oi.data(), od.data());
+      if (rc == RG_OK && start)
+        for (auto &v : oi) v += (int32_t)start;  // start_id of this part (:413); inside the part the shards are already offset
+    } else {
+      rc = rg_knn(base.data(), np, queries.data(), nq, (uint32_t)dim, (uint32_t)Kp, metric, (int32_t)start, oi.data(), od.data());
+    }
     if (rc != RG_OK) throw std::runtime_error(rg_last_error());
     if (parts == 1) {
       if (Kp != K) throw std::runtime_error("K exceeds the number of base points");
@@ -110,6 +125,7 @@ static int aux_main(const std::string &base_file, const std::string &query_file,
       }
     }
   }
+  if (group) rg_group_destroy(group);
   auto t1 = std::chrono::high_resolution_clock::now();
   const double sec = std::chrono::duration<double>(t1 - t0).count();
   std::cout << "kNN of " << nq << " queries x " << total << " points, K=" << K << ": " << sec << " s, "
@@ -135,7 +151,8 @@ int main(int argc, char **argv) {
       .add("query_file", "File containing the query vectors in binary format", true)
       .add("gt_file", "File name for the writing ground truth in binary format", true)
       .add("K", "Number of ground truth nearest neighbors to compute", true).numeric()
-      .add("tags_file", "File containing the tags in binary format", false);
+      .add("tags_file", "File containing the tags in binary format", false)
+      .add("gpus", "GPUs of this box the base parts are sharded over (one NCCL rank per GPU inside this process)", false, false, "1").numeric();
   try {
     if (args.parse(argc, argv)) return 0;
   } catch (const std::exception &ex) {
@@ -161,9 +178,11 @@ int main(int argc, char **argv) {
   }
   try {
     const uint64_t K = args.u64("K");
-    if (data_type == "float") return aux_main<float>(args.str("base_file"), args.str("query_file"), args.str("gt_file"), K, metric);
-    if (data_type == "int8") return aux_main<int8_t>(args.str("base_file"), args.str("query_file"), args.str("gt_file"), K, metric);
-    return aux_main<uint8_t>(args.str("base_file"), args.str("query_file"), args.str("gt_file"), K, metric);
+    const int gpus = (int)args.u64("gpus");
+    if (gpus < 1) throw std::runtime_error("--gpus must be at least 1");
+    if (data_type == "float") return aux_main<float>(args.str("base_file"), args.str("query_file"), args.str("gt_file"), K, metric, gpus);
+    if (data_type == "int8") return aux_main<int8_t>(args.str("base_file"), args.str("query_file"), args.str("gt_file"), K, metric, gpus);
+    return aux_main<uint8_t>(args.str("base_file"), args.str("query_file"), args.str("gt_file"), K, metric, gpus);
   } catch (const std::exception &e) {
     std::cout << std::string(e.what()) << std::endl;
     std::cerr << "Compute GT failed." << std::endl;

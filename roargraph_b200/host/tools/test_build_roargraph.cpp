@@ -19,6 +19,7 @@ int main(int argc, char **argv) {
       .add("M_sq", "Number of neighbors for sampled query points to build the bipartite graph", false, false, "32").numeric()
       .add("M_pjbp", "Number of neighbors for projection graph", false, false, "32").numeric()
       .add("L_pjpq", "Priority queue length for projection graph searching", false, false, "32").numeric()
+      .add("gpus", "GPUs of this box the base rows are sharded over: one index per shard, files <path>.shard<s>of<N>", false, false, "1").numeric()
       .add("build_rounds", "bulk-synchronous rounds of the connectivity phase (0 = automatic)", false, false, "0").numeric()
       .add("num_threads", "Number of host threads (kept for compatibility; the build runs on the GPU)", false, false,
            std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T').numeric();
@@ -58,13 +59,27 @@ int main(int argc, char **argv) {
       return -1;
     }
     efanna2e::IndexBipartite index(padded, base_num, dist_metric, nullptr);
-    index.LoadLearnBaseKNN(args.str("learn_base_nn_path").c_str());
+    const uint32_t gpus = (uint32_t)args.u64("gpus");
+    index.SetGpus(gpus);
+    float *data_sq = nullptr;
+    if (gpus > 1) {
+      // a shard's graph is built from the training queries' neighbours INSIDE the shard, computed on its GPU from the
+      // training vectors; the learn-base kNN file (neighbours over the whole base) is not read
+      efanna2e::load_data<float>(args.str("sampled_query_data_path").c_str(), sq_num, sq_dim, data_sq);
+      unsigned sq_padded = sq_dim;
+      data_sq = efanna2e::data_align(data_sq, sq_num, sq_padded);
+      if (sq_padded != padded) throw std::runtime_error("base and query dimension mismatch");
+      if (dist_metric == efanna2e::COSINE) efanna2e::normalize_rows(data_sq, sq_num, sq_padded);
+    } else {
+      index.LoadLearnBaseKNN(args.str("learn_base_nn_path").c_str());
+    }
     auto s = std::chrono::high_resolution_clock::now();
-    index.BuildRoarGraph(sq_num, nullptr, base_num, data_bp, parameters);
+    index.BuildRoarGraph(sq_num, data_sq, base_num, data_bp, parameters);
     auto e = std::chrono::high_resolution_clock::now();
     std::cout << "indexing time: " << std::chrono::duration<double>(e - s).count() << "\n";
     index.SaveProjectionGraph(args.str("projection_index_save_path").c_str());
     free(data_bp);
+    free(data_sq);
   } catch (const std::exception &ex) {
     std::cerr << ex.what() << '\n';
     return -1;

@@ -35,6 +35,7 @@ int main(int argc, char **argv) {
       .add("L_pq", "Priority queue length for searching", true, true).numeric()
       .add("k", "k nearest neighbors", true, false, "1").numeric()
       .add("evaluation_save_path", "Path prefix for saving evaluation results", false)
+      .add("gpus", "GPUs of this box the base rows are sharded over (per-shard index files <path>.shard<s>of<N>)", false, false, "1").numeric()
       .add("num_threads", "Number of host threads (kept for compatibility; the search runs on the GPU)", false, false,
            std::to_string(std::max(1u, std::thread::hardware_concurrency())), 'T').numeric();
   try {
@@ -78,11 +79,13 @@ int main(int argc, char **argv) {
       std::cout << "Unknown distance type: " << dist << std::endl;
       return -1;
     }
-    if (!std::filesystem::exists(index_file)) {
+    const uint32_t gpus = (uint32_t)args.u64("gpus");
+    if (!std::filesystem::exists(gpus > 1 ? efanna2e::IndexBipartite::ShardFile(index_file, 0, gpus) : index_file)) {
       std::cout << "projection index file does not exist." << std::endl;
       return -1;
     }
     efanna2e::IndexBipartite index(q_dim, base_num, dist_metric, nullptr);
+    index.SetGpus(gpus);
     index.LoadSearchNeededData(base_data_file.c_str(), "");
     std::cout << "Load graph index: " << index_file << std::endl;
     index.LoadProjectionGraph(index_file.c_str());
@@ -125,6 +128,10 @@ int main(int argc, char **argv) {
       uint64_t t_cmps, t_hops, t_adj;
       index.LastSearchStats(t_cmps, t_hops, t_adj);
       const double gbs = ((double)(t_cmps + q_pts) * q_dim * 4.0 + (double)t_adj * 4.0) / (us * 1e-6) / 1e9;
+      if (gpus > 1) {  // summed over the shards: every query runs on every shard
+        sum_cmps = (double)t_cmps;
+        sum_hops = (double)t_hops;
+      }
       const float avg_cmps = (float)(sum_cmps / q_pts), avg_hops = (float)(sum_hops / q_pts);
       std::cout << L_pq << "\t\t" << qps << "\t\t" << avg_cmps << "\t\t" << (ms / q_pts) << "\t\t" << recall << "\t\t"
                 << avg_hops << "\t\t" << gbs << std::endl;

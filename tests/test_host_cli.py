@@ -390,3 +390,65 @@ def test_reference_build_and_bipartite_mains_on_the_mirror(tmp_path, golden):
                         "--k", "5", "-T", "4"], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert _bipartite_table(p.stdout)[200][3] > 0.6
+
+
+# ---- --gpus N: the base rows sharded over the GPUs of the box inside ONE process (rg_group_* / rg_sharded_*) ----------------
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G", [2, 4])
+def test_sharded_clis_build_search_groundtruth(tmp_path, oracle, G):
+    """test_build_roargraph --gpus G writes one reference-format index file per shard (local ids); test_search_roargraph
+    --gpus G searches every shard and merges: its recall column equals the CPU oracle run on every shard file and merged on the
+    host by (distance, id); compute_groundtruth --gpus G writes the file the single-GPU run writes."""
+    if _gpu_count() < G:
+        pytest.skip(f"needs {G} GPUs")
+    from roargraph_b200 import synth
+    nb, dim, k = 20000, 96, 10
+    base, train, test = synth.make_numpy(nb, 5000, 128, dim, seed=31)
+    bf, tf, qf, gf, xf = (str(tmp_path / n) for n in ("base.fbin", "train.fbin", "query.fbin", "gt.bin", "index.rg"))
+    F.write_fbin(bf, base)
+    F.write_fbin(tf, train)
+    F.write_fbin(qf, test)
+    # ground truth: sharded tool run == single-GPU tool run
+    g1 = str(tmp_path / "gt1.bin")
+    for out, gpus in ((gf, G), (g1, 1)):
+        p = run("compute_groundtruth", "--data_type", "float", "--dist_fn", "l2", "--base_file", bf, "--query_file", qf,
+                "--gt_file", out, "--K", 20, "--gpus", gpus)
+        assert p.returncode == 0, p.stdout + p.stderr
+    (ia, da), (ib, db) = F.read_truthset(gf), F.read_truthset(g1)
+    assert (ia == ib).mean() > 0.999 and np.allclose(da, db, rtol=1e-5, atol=1e-5)
+    p = run("test_build_roargraph", "--data_type", "float", "--dist", "l2", "--base_data_path", bf, "--sampled_query_data_path",
+            tf, "--projection_index_save_path", xf, "--learn_base_nn_path", str(tmp_path / "unused.gt"), "--M_sq", 64, "--M_pjbp",
+            24, "--L_pjpq", 200, "--gpus", G)
+    assert p.returncode == 0, p.stdout + p.stderr
+    Ls = [10, 40, 150]
+    p = run("test_search_roargraph", "--data_type", "float", "--dist", "l2", "--base_data_path", bf, "--query_path", qf,
+            "--gt_path", gf, "--projection_index_save_path", xf, "--L_pq", *Ls, "--k", k, "--gpus", G)
+    assert p.returncode == 0, p.stdout + p.stderr
+    t = _table(p.stdout)
+    assert sorted(t) == Ls
+    b, q = F.pad_rows(base), F.pad_rows(test)
+    for L in Ls:
+        parts_i, parts_d, cm = [], [], 0.0
+        for s in range(G):
+            lo, hi = s * nb // G, (s + 1) * nb // G
+            ep, row_off, nbrs = F.read_projection_index(f"{xf}.shard{s}of{G}")
+            assert len(row_off) == hi - lo + 1 and (nbrs < hi - lo).all()
+            r = oracle.search_roargraph(b[lo:hi], row_off, nbrs, ep, "l2", q, k, L)
+            parts_i.append(r["ids"].astype(np.int64) + lo)
+            parts_d.append(r["dists"])
+            cm += float(r["cmps"].mean())
+        ai, ad = np.concatenate(parts_i, 1), np.concatenate(parts_d, 1)
+        order = np.lexsort((ai, ad), axis=1)[:, :k]
+        merged = np.take_along_axis(ai, order, 1)
+        hit = sum(int((merged == ia[:, j:j + 1]).any(axis=1).sum()) for j in range(k))
+        assert t[L][3] == pytest.approx(hit / float(k * len(q)), abs=1e-6), (L, t[L])   # recall
+        assert t[L][1] == pytest.approx(cm, rel=1e-5), (L, t[L], cm)                     # avg cmps summed over the shards
