@@ -168,6 +168,7 @@ class ShardedRoarIndex:
             per = -(-nq // self.world)
             self._buf[key] = dict(
                 d_q=torch.empty((self.world * per, dim), dtype=torch.float32, device=device),
+                d_mine=torch.zeros((per, dim), dtype=torch.float32, device=device),
                 d_i=torch.empty((nq, k), dtype=torch.int32, device=device),
                 d_d=torch.empty((nq, k), dtype=torch.float32, device=device),
                 h_i=torch.empty((nq, k), dtype=torch.int32).pin_memory(),
@@ -190,7 +191,7 @@ class ShardedRoarIndex:
         if self.world > 1:
             per = -(-nq // self.world)
             lo, hi = min(self.rank * per, nq), min((self.rank + 1) * per, nq)
-            mine = b["d_q"][self.rank * per:self.rank * per + per]
+            mine = b["d_mine"]
             if hi > lo:
                 mine[:hi - lo].copy_(q[lo:hi], non_blocking=True)
             dist.all_gather_into_tensor(b["d_q"], mine, group=self.group)
