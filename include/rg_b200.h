@@ -60,6 +60,15 @@ int rg_device_sm_count(void);
  * Replaces: IndexBipartite ctor + LoadSearchNeededData (include/index_bipartite.h:27,62). */
 int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim, int metric, int base_on_device);
 
+/* The same from an fbin file (u32 n, u32 d, n*d f32; README.md:14, include/efanna2e/util.h:107-211), streamed: the file is read
+ * in 64 MB slabs into two pinned staging buffers; each slab is handed to `hook` (optional; rows of the file's UNPADDED dim,
+ * e.g. the reference's normalize<float> for COSINE, src/index_bipartite.cpp:2679-2684) and copied to HBM asynchronously
+ * while the next slab is being read, the rows zero-padded to x8 floats by the copy itself (util.h:37-75).  Replaces
+ * load_data + data_align + the pageable 8-20 GB host copy of LoadVectorData.  out_nd / out_dim (padded) may be NULL. */
+typedef void (*rg_row_hook)(float *rows, uint64_t n, uint32_t dim, void *user);
+int rg_index_create_from_fbin(rg_index **out, const char *path, int metric, rg_row_hook hook, void *user, uint64_t *out_nd,
+                              uint32_t *out_dim);
+
 /* Projection graph as host CSR (row_off[nd+1], nbrs[row_off[nd]]) + entry point, i.e. the content of
  * IndexBipartite::GetProjectionGraph() / LoadProjectionGraph (src/index_bipartite.cpp:2097-2117). */
 int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, const uint32_t *nbrs);

@@ -91,22 +91,183 @@ __device__ __forceinline__ bool list_has(const uint32_t *list, uint32_t n, uint3
 
 // Shared-memory layout (dynamic): keys[kMaxCand] u64 | raw ids[kMaxCand] | own[128] | skip[128] | result[128] |
 // vrow[dim] | prow[dim] | sel[M * dim]
+struct PruneSmem {
+    unsigned long long *keys;
+    uint32_t *raw, *own, *skip, *result;
+    float *vrow, *prow, *sel;
+};
+
+// The occlusion prune shared by every phase (:1871-1890 and its siblings): raw[0..n) candidate ids of node v (keys already
+// hold (distance to v, id) when have_dists) -> sorted by (distance, id), greedy scan "candidate j is dropped when a selected
+// row is closer to it than v is", at most cap survivors, optionally padded back to cap with the nearest remaining
+// candidates (`fill`).  result[0..returned) = the new list.  Called by the whole CTA.
+__device__ uint32_t prune_candidates(const PruneParams &p, const PruneSmem &sm, uint32_t v, uint32_t n, uint32_t cap, bool fill,
+                                     bool have_dists, uint32_t n_skip) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t dim4 = p.dim >> 2;
+    unsigned long long *keys = sm.keys;
+    if (!have_dists) {
+        for (uint32_t c = warp; c < n; c += kPruneThreads / 32) {
+            const uint32_t id = sm.raw[c];
+            if (id >= p.nd) {  // not a base row (e.g. a -1 filler in a short kNN list)
+                if (lane == 0) keys[c] = ~0ull;
+                continue;
+            }
+            const float d = warp_distance(p.base + (size_t)id * p.dim, sm.vrow, dim4, p.l2, lane);
+            if (lane == 0) keys[c] = ((unsigned long long)f2ord(d) << 32) | id;
+        }
+    }
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    for (uint32_t i = n + tid; i < m; i += kPruneThreads) keys[i] = ~0ull;
+    __syncthreads();
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (m >> 1); i += kPruneThreads) {
+                const uint32_t lo = 2 * i - (i & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // greedy occlusion scan over the sorted candidates
+    uint32_t nres = 0;
+    uint32_t prev = 0xffffffffu;
+    for (uint32_t i = 0; i < n && nres < cap; ++i) {
+        const unsigned long long key = keys[i];
+        const uint32_t id = (uint32_t)key;
+        if (id == v || id == prev || id >= p.nd) continue;
+        prev = id;
+        if (nres == 0 && n_skip && list_has(sm.skip, n_skip, id)) continue;
+        const float pd = ord2f((uint32_t)(key >> 32));
+        for (uint32_t j = tid; j < dim4; j += kPruneThreads)
+            reinterpret_cast<float4 *>(sm.prow)[j] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)id * p.dim) + j);
+        __syncthreads();
+        int occ = 0;
+        for (uint32_t r = warp; r < nres; r += kPruneThreads / 32) {
+            const float djk = warp_distance(sm.prow, sm.sel + (size_t)r * p.dim, dim4, p.l2, lane);
+            if (djk < pd) {
+                occ = 1;
+                break;
+            }
+        }
+        occ = __syncthreads_or(occ);
+        if (!occ) {
+            for (uint32_t j = tid; j < dim4; j += kPruneThreads)
+                reinterpret_cast<float4 *>(sm.sel + (size_t)nres * p.dim)[j] = reinterpret_cast<const float4 *>(sm.prow)[j];
+            if (tid == 0) sm.result[nres] = id;
+            ++nres;
+        }
+        __syncthreads();
+    }
+    if (fill) {  // pad with the nearest remaining candidates (:1680-1688, :1603-1607); every thread computes the same count
+        __shared__ uint32_t s_fill;
+        if (tid == 0) {
+            uint32_t pv = 0xffffffffu, nr = nres;
+            for (uint32_t i = 0; i < n && nr < cap; ++i) {
+                const uint32_t id = (uint32_t)keys[i];
+                if (id == v || id == pv || id >= p.nd) continue;
+                pv = id;
+                if (!list_has(sm.result, nr, id)) sm.result[nr++] = id;
+            }
+            s_fill = nr;
+        }
+        __syncthreads();
+        nres = s_fill;
+    }
+    __syncthreads();
+    return nres;
+}
+
 __global__ void __launch_bounds__(kPruneThreads) prune_kernel(const PruneParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
-    uint32_t *raw = reinterpret_cast<uint32_t *>(keys + kMaxCand);
-    uint32_t *own = raw + kMaxCand;
-    uint32_t *skip = own + 128;
-    uint32_t *result = skip + 128;
-    float *vrow = reinterpret_cast<float *>(result + 128);
-    float *prow = vrow + p.dim;
-    float *sel = prow + p.dim;
-    __shared__ uint32_t s_cnt, s_warp_tot[4];
+    PruneSmem sm;
+    sm.keys = reinterpret_cast<unsigned long long *>(smem);
+    sm.raw = reinterpret_cast<uint32_t *>(sm.keys + kMaxCand);
+    sm.own = sm.raw + kMaxCand;
+    sm.skip = sm.own + 128;
+    sm.result = sm.skip + 128;
+    sm.vrow = reinterpret_cast<float *>(sm.result + 128);
+    sm.prow = sm.vrow + p.dim;
+    sm.sel = sm.prow + p.dim;
+    unsigned long long *keys = sm.keys;
+    uint32_t *raw = sm.raw, *own = sm.own, *skip = sm.skip, *result = sm.result;
+    __shared__ uint32_t s_n, s_pos_lo, s_more;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const uint32_t v = p.node_lo + blockIdx.x;
     const uint32_t dim4 = p.dim >> 2;
     const uint32_t M = p.M;
+
+    if (p.mode == 2 || p.mode == 4) {
+        // Reverse edges (ProjectionAddReverse :1394-1432, SupplyAddReverse :1352-1392) replayed in the reference's order: the
+        // offers of this round reach node v in ascending source id (the reference walks the sources in id order); a source not
+        // yet in the list is appended while the list has room (cap = M_pjbp for the projection graph, 2 * M_pjbp for the
+        // supply graph); the first one that does not fit triggers a prune of list + that source back to <= M_pjbp, after which
+        // the list has room again.  (One prune over list + ALL offers — what a bulk-synchronous round suggests — leaves every
+        // busy list at <= M_pjbp and loses 6 % of the final degree against the reference.)
+        uint32_t *grow = (p.mode == 2) ? p.proj + (size_t)v * p.proj_stride : p.supply + (size_t)v * p.supply_stride;
+        const uint32_t keep_cap = (p.mode == 2) ? M : 2 * M;
+        const uint64_t ib = p.in_off[v], ie = p.in_off[v + 1];
+        if (ib == ie) return;
+        const uint32_t n_own = min(grow[0], 128u);
+        for (uint32_t i = tid; i < n_own; i += kPruneThreads) raw[i] = grow[1 + i];
+        for (uint32_t i = tid; i < dim4; i += kPruneThreads)
+            reinterpret_cast<float4 *>(sm.vrow)[i] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)v * p.dim) + i);
+        if (tid == 0) {
+            s_n = n_own;
+            s_pos_lo = 0;
+        }
+        __syncthreads();
+        const uint32_t n_off = (uint32_t)min((uint64_t)0xffffffffu, ie - ib);
+        bool changed = false;
+        for (;;) {
+            if (tid == 0) {  // append phase: offers in order, until the list is full and one more distinct source is waiting
+                uint32_t n = s_n, pos = s_pos_lo, more = 0;
+                while (pos < n_off) {
+                    const uint32_t src = (uint32_t)p.in_keys[ib + pos];
+                    if (src == v || list_has(raw, n, src)) {
+                        ++pos;
+                        continue;
+                    }
+                    if (n < keep_cap) {
+                        raw[n++] = src;
+                        ++pos;
+                        continue;
+                    }
+                    raw[n] = src;  // does not fit: prune list + this source
+                    more = 1;
+                    ++pos;
+                    break;
+                }
+                s_n = n;
+                s_pos_lo = pos;
+                s_more = more;
+            }
+            __syncthreads();
+            const uint32_t n = s_n;
+            if (n != n_own) changed = true;
+            if (!s_more) break;
+            const uint32_t nres = prune_candidates(p, sm, v, n + 1, M, /*fill=*/p.mode == 2, false, 0);
+            for (uint32_t i = tid; i < nres; i += kPruneThreads) raw[i] = result[i];
+            if (tid == 0) s_n = nres;
+            changed = true;
+            __syncthreads();
+        }
+        if (changed) {
+            const uint32_t n = s_n;
+            for (uint32_t i = tid; i < n; i += kPruneThreads) grow[1 + i] = raw[i];
+            __syncthreads();
+            if (tid == 0) grow[0] = n;
+        }
+        return;
+    }
 
     uint32_t n = 0;        // candidates in raw[]
     uint32_t n_skip = 0;   // skip list (first pick must not already be a projection neighbour, :1859-1862)
@@ -137,142 +298,29 @@ __global__ void __launch_bounds__(kPruneThreads) prune_kernel(const PruneParams 
         target = p.supply + (size_t)v * p.supply_stride;
         target_cap = M;
     } else {
-        // modes 2, 4, 5: own list (+ incoming reverse offers)
-        uint32_t *grow = (p.mode == 2) ? p.proj + (size_t)v * p.proj_stride : p.supply + (size_t)v * p.supply_stride;
-        const uint32_t keep_cap = (p.mode == 2) ? M : 2 * M;  // :1360 SupplyAddReverse works with M_pjbp * 2
+        // mode 5: supply lists above M_pjbp re-pruned (:1224-1247)
+        uint32_t *grow = p.supply + (size_t)v * p.supply_stride;
         const uint32_t n_own = min(grow[0], 128u);
-        uint64_t ib = 0, ie = 0;
-        if (p.mode != 5) {
-            ib = p.in_off[v];
-            ie = p.in_off[v + 1];
-            if (ib == ie) return;
-        } else {
-            if (n_own <= M) return;
-            const uint32_t *prow_ = p.proj + (size_t)v * p.proj_stride;
-            n_skip = min(prow_[0], 128u);
-            for (uint32_t i = tid; i < n_skip; i += kPruneThreads) skip[i] = prow_[1 + i];
-        }
+        if (n_own <= M) return;
+        const uint32_t *prow_ = p.proj + (size_t)v * p.proj_stride;
+        n_skip = min(prow_[0], 128u);
+        for (uint32_t i = tid; i < n_skip; i += kPruneThreads) skip[i] = prow_[1 + i];
         for (uint32_t i = tid; i < n_own; i += kPruneThreads) {
             own[i] = grow[1 + i];
             raw[i] = own[i];
         }
-        if (tid == 0) s_cnt = n_own;
-        __syncthreads();
-        // ordered compaction of the offers that are new to this list
-        for (uint64_t c0 = ib; c0 < ie; c0 += kPruneThreads) {
-            const uint64_t j = c0 + tid;
-            uint32_t src = 0;
-            bool isnew = false;
-            if (j < ie) {
-                src = (uint32_t)p.in_keys[j];
-                isnew = src != v && !list_has(own, n_own, src);
-            }
-            const uint32_t bal = __ballot_sync(kFullMask, isnew);
-            if (lane == 0) s_warp_tot[warp] = __popc(bal);
-            __syncthreads();
-            uint32_t off = s_cnt;
-            for (int w2 = 0; w2 < warp; ++w2) off += s_warp_tot[w2];
-            off += __popc(bal & ((1u << lane) - 1u));
-            if (isnew && off < kMaxCand) raw[off] = src;
-            __syncthreads();
-            if (tid == 0) s_cnt = min(s_cnt + s_warp_tot[0] + s_warp_tot[1] + s_warp_tot[2] + s_warp_tot[3], kMaxCand);
-            __syncthreads();
-            if (s_cnt >= kMaxCand) break;
-        }
-        n = s_cnt;
-        if (p.mode != 5) {
-            if (n == n_own) return;  // nothing new
-            if (n <= keep_cap) {     // room left: plain append (:1364-1366 / :1401-1403)
-                for (uint32_t i = n_own + tid; i < n; i += kPruneThreads) grow[1 + i] = raw[i];
-                __syncthreads();
-                if (tid == 0) grow[0] = n;
-                return;
-            }
-        }
-        fill = (p.mode == 2);  // PruneProjectionReverseCandidates pads back to M_pjbp (:1603-1607); the supply variants do not
+        n = n_own;
         target = grow;
         target_cap = M;
     }
     __syncthreads();
-
     // the node's own row
     for (uint32_t i = tid; i < dim4; i += kPruneThreads)
-        reinterpret_cast<float4 *>(vrow)[i] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)v * p.dim) + i);
+        reinterpret_cast<float4 *>(sm.vrow)[i] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)v * p.dim) + i);
     __syncthreads();
-    if (!have_dists) {
-        for (uint32_t c = warp; c < n; c += kPruneThreads / 32) {
-            const uint32_t id = raw[c];
-            if (id >= p.nd) {  // not a base row (e.g. a -1 filler in a short kNN list)
-                if (lane == 0) keys[c] = ~0ull;
-                continue;
-            }
-            const float d = warp_distance(p.base + (size_t)id * p.dim, vrow, dim4, p.l2, lane);
-            if (lane == 0) keys[c] = ((unsigned long long)f2ord(d) << 32) | id;
-        }
-    }
-    uint32_t m = 1;
-    while (m < n) m <<= 1;
-    for (uint32_t i = n + tid; i < m; i += kPruneThreads) keys[i] = ~0ull;
-    __syncthreads();
-    for (uint32_t size = 2; size <= m; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t i = tid; i < (m >> 1); i += kPruneThreads) {
-                const uint32_t lo = 2 * i - (i & (stride - 1));
-                const uint32_t hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const unsigned long long a = keys[lo], b = keys[hi];
-                if ((a > b) == up) {
-                    keys[lo] = b;
-                    keys[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
-
-    // greedy occlusion scan over the sorted candidates (:1871-1890 and its siblings)
-    uint32_t nres = 0;
-    uint32_t prev = 0xffffffffu;
-    for (uint32_t i = 0; i < n && nres < target_cap; ++i) {
-        const unsigned long long key = keys[i];
-        const uint32_t id = (uint32_t)key;
-        if (id == v || id == prev || id >= p.nd) continue;
-        prev = id;
-        if (nres == 0 && n_skip && list_has(skip, n_skip, id)) continue;
-        const float pd = ord2f((uint32_t)(key >> 32));
-        for (uint32_t j = tid; j < dim4; j += kPruneThreads)
-            reinterpret_cast<float4 *>(prow)[j] = __ldg(reinterpret_cast<const float4 *>(p.base + (size_t)id * p.dim) + j);
-        __syncthreads();
-        int occ = 0;
-        for (uint32_t r = warp; r < nres; r += kPruneThreads / 32) {
-            const float djk = warp_distance(prow, sel + (size_t)r * p.dim, dim4, p.l2, lane);
-            if (djk < pd) {
-                occ = 1;
-                break;
-            }
-        }
-        occ = __syncthreads_or(occ);
-        if (!occ) {
-            for (uint32_t j = tid; j < dim4; j += kPruneThreads)
-                reinterpret_cast<float4 *>(sel + (size_t)nres * p.dim)[j] = reinterpret_cast<const float4 *>(prow)[j];
-            if (tid == 0) result[nres] = id;
-            ++nres;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        if (fill) {  // pad with the nearest remaining candidates (:1680-1688, :1603-1607)
-            uint32_t pv = 0xffffffffu;
-            for (uint32_t i = 0; i < n && nres < target_cap; ++i) {
-                const uint32_t id = (uint32_t)keys[i];
-                if (id == v || id == pv || id >= p.nd) continue;
-                pv = id;
-                if (!list_has(result, nres, id)) result[nres++] = id;
-            }
-        }
-        target[0] = nres;
-        for (uint32_t i = 0; i < nres; ++i) target[1 + i] = result[i];
-    }
+    const uint32_t nres = prune_candidates(p, sm, v, n, target_cap, fill, have_dists, n_skip);
+    if (tid == 0) target[0] = nres;
+    for (uint32_t i = tid; i < nres; i += kPruneThreads) target[1 + i] = result[i];
 }
 
 __global__ void owner_kernel(const uint32_t *knn, uint32_t knn_stride, uint64_t nsq, uint32_t nd, int *owner) {

@@ -227,6 +227,79 @@ int rg_index_create(rg_index **out, const float *base, uint64_t nd, uint32_t dim
     return RG_OK;
 }
 
+int rg_index_create_from_fbin(rg_index **out, const char *path, int metric, rg_row_hook hook, void *user, uint64_t *out_nd,
+                              uint32_t *out_dim) {
+    if (!out || !path) { set_error("rg_index_create_from_fbin: null argument"); return RG_EINVAL; }
+    int rc = ensure_device();
+    if (rc != RG_OK) return rc;
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error(std::string("rg_index_create_from_fbin: cannot open ") + path); return RG_EINVAL; }
+    uint32_t hdr[2] = {0, 0};
+    if (fread(hdr, 4, 2, f) != 2 || hdr[0] == 0 || hdr[1] == 0) {
+        fclose(f);
+        set_error("Data file size wrong!");  // util.h:124
+        return RG_EINVAL;
+    }
+    const uint64_t nd = hdr[0];
+    const uint32_t dim = hdr[1], pdim = (dim + 7u) & ~7u;  // rows padded to x8 floats with zeros (util.h:37-75, :191-199)
+    fseek(f, 0, SEEK_END);
+    const uint64_t fsize = (uint64_t)ftell(f);
+    if (fsize != 8 + nd * dim * sizeof(float)) {
+        fclose(f);
+        set_error("Data file size wrong!");
+        return RG_EINVAL;
+    }
+    fseek(f, 8, SEEK_SET);
+    float *d_base = nullptr;
+    cudaError_t e = cudaMalloc(&d_base, nd * pdim * sizeof(float));
+    if (e == cudaSuccess && pdim != dim) e = cudaMemset(d_base, 0, nd * pdim * sizeof(float));
+    const uint64_t slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(nd, (64ull << 20) / ((uint64_t)dim * 4u)));
+    float *pin[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaMallocHost(&pin[b], slab_rows * dim * sizeof(float));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    }
+    bool short_read = false;
+    int slab = 0;
+    for (uint64_t r0 = 0; r0 < nd && e == cudaSuccess; r0 += slab_rows, slab ^= 1) {
+        const uint64_t n = std::min(slab_rows, nd - r0);
+        e = cudaEventSynchronize(done[slab]);  // the copy that last used this staging buffer has finished
+        if (e != cudaSuccess) break;
+        if (fread(pin[slab], sizeof(float) * dim, n, f) != n) { short_read = true; break; }
+        if (hook) hook(pin[slab], n, dim, user);  // e.g. the reference's normalize<float> per row for COSINE
+        // pitch conversion on the copy engine: file rows of dim floats -> device rows of pdim floats (padding stays zero)
+        e = cudaMemcpy2DAsync(d_base + r0 * pdim, (size_t)pdim * 4, pin[slab], (size_t)dim * 4, (size_t)dim * 4, n,
+                              cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[slab], st);
+    }
+    if (e == cudaSuccess && !short_read) e = cudaStreamSynchronize(st);
+    fclose(f);
+    for (int b = 0; b < 2; ++b) {
+        if (pin[b]) cudaFreeHost(pin[b]);
+        if (done[b]) cudaEventDestroy(done[b]);
+    }
+    if (st) cudaStreamDestroy(st);
+    if (e != cudaSuccess || short_read) {
+        if (d_base) cudaFree(d_base);
+        if (short_read) { set_error("Data file size wrong!"); return RG_EINVAL; }
+        return cuda_fail(e, "rg_index_create_from_fbin");
+    }
+    rg_index *idx = nullptr;
+    rc = rg_index_create(&idx, d_base, nd, pdim, metric, 1);
+    if (rc != RG_OK) {
+        cudaFree(d_base);
+        return rc;
+    }
+    idx->own_base = true;  // the index frees what this function allocated
+    *out = idx;
+    if (out_nd) *out_nd = nd;
+    if (out_dim) *out_dim = pdim;
+    return RG_OK;
+}
+
 int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, const uint32_t *nbrs) {
     if (!idx || !row_off || (!nbrs && row_off[idx->nd] != 0)) { set_error("rg_index_set_graph: null argument"); return RG_EINVAL; }
     if (ep >= idx->nd) { set_error("rg_index_set_graph: entry point out of range"); return RG_EINVAL; }
@@ -243,24 +316,68 @@ int rg_index_set_graph(rg_index *idx, uint32_t ep, const uint64_t *row_off, cons
     }
     if (max_deg > 4096) { set_error("rg_index_set_graph: out-degree above 4096 is not supported by the fixed-stride layout"); return RG_EINVAL; }
     const uint32_t stride = (max_deg + 1 + 7) & ~7u;  // [deg, ids...] padded to whole 32-byte sectors
-    std::vector<uint32_t> host((size_t)nd * stride, 0xffffffffu);
-    for (uint64_t u = 0; u < nd; ++u) {
-        uint32_t *row = host.data() + (size_t)u * stride;
-        uint32_t d = 0;
-        for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
-            const uint32_t v = nbrs[j];
-            if (v >= nd) { set_error("rg_index_set_graph: neighbour id out of range"); return RG_EINVAL; }
-            bool dup = false;
-            for (uint32_t i = 0; i < d; ++i)
-                if (row[1 + i] == v) { dup = true; break; }
-            if (!dup) row[1 + d++] = v;
-        }
-        row[0] = d;
-    }
     if (idx->d_adj) cudaFree(idx->d_adj);
     idx->d_adj = nullptr;
-    RG_CUDA(cudaMalloc(&idx->d_adj, host.size() * sizeof(uint32_t)));
-    RG_CUDA(cudaMemcpy(idx->d_adj, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RG_CUDA(cudaMalloc(&idx->d_adj, (size_t)nd * stride * sizeof(uint32_t)));
+    // CSR -> fixed-stride rows in slabs: the host threads fill one pinned slab while the previous one is on its way to HBM
+    // (a 10 M-node graph is 2.9 GB of rows; built single-threaded in pageable memory it cost more than the search sweep)
+    const uint64_t slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(nd, (64ull << 20) / ((uint64_t)stride * 4u)));
+    uint32_t *pin[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaMallocHost(&pin[b], slab_rows * stride * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    }
+    const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<uint32_t> max_dedup(nt, 0);
+    std::vector<int> bad(nt, 0);
+    int slab = 0;
+    for (uint64_t u0 = 0; u0 < nd && e == cudaSuccess; u0 += slab_rows, slab ^= 1) {
+        const uint64_t n = std::min(slab_rows, nd - u0);
+        e = cudaEventSynchronize(done[slab]);  // the copy that last used this slab has finished
+        if (e != cudaSuccess) break;
+        uint32_t *host = pin[slab];
+        std::vector<std::thread> th;
+        const uint64_t per = (n + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t]() {
+                const uint64_t a = std::min<uint64_t>((uint64_t)t * per, n), b = std::min<uint64_t>(a + per, n);
+                for (uint64_t i = a; i < b; ++i) {
+                    const uint64_t u = u0 + i;
+                    uint32_t *row = host + (size_t)i * stride;
+                    uint32_t d = 0;
+                    for (uint64_t j = row_off[u]; j < row_off[u + 1]; ++j) {
+                        const uint32_t v = nbrs[j];
+                        if (v >= nd) { bad[t] = 1; continue; }
+                        bool dup = false;
+                        for (uint32_t q = 0; q < d; ++q)
+                            if (row[1 + q] == v) { dup = true; break; }
+                        if (!dup) row[1 + d++] = v;
+                    }
+                    row[0] = d;
+                    for (uint32_t q = d + 1; q < stride; ++q) row[q] = 0xffffffffu;
+                    max_dedup[t] = std::max(max_dedup[t], d);
+                }
+            });
+        for (auto &x : th) x.join();
+        e = cudaMemcpyAsync(idx->d_adj + (size_t)u0 * stride, host, n * stride * sizeof(uint32_t), cudaMemcpyHostToDevice, idx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[slab], idx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+    for (int b = 0; b < 2; ++b) {
+        if (pin[b]) cudaFreeHost(pin[b]);
+        if (done[b]) cudaEventDestroy(done[b]);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "rg_index_set_graph: adjacency upload");
+    for (unsigned t = 0; t < nt; ++t)
+        if (bad[t]) {
+            cudaFree(idx->d_adj);
+            idx->d_adj = nullptr;
+            idx->has_graph = false;
+            set_error("rg_index_set_graph: neighbour id out of range");
+            return RG_EINVAL;
+        }
     idx->adj_stride = stride;
     idx->max_deg = max_deg;
     idx->ep = ep;

@@ -666,6 +666,15 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
     // the expected survivors per chunk stay near K
     const uint64_t n_seed = tc ? knn_tc_seed_rows(nb, K) : 0;
     const uint64_t chunk0 = tc ? 256u : cap;
+    // Largest chunk.  The re-rank after a chunk gathers fp32 rows of THAT chunk only, and a row is wanted by many queries of
+    // the batch (151 552 queries x ~K/8 survivors over ~10^5 rows: tens of reads per row), so a chunk whose fp32 rows fit in
+    // L2 turns the gather from HBM-bound into L2-bound — and tau tightens more often (fewer survivors overall).
+    // RG_KNN_CHUNK_MAX overrides (rows, rounded down to 256).
+    uint64_t chunk_max = 1ull << 22;
+    if (tc) {
+        chunk_max = std::max<uint64_t>(16384u, ((80ull << 20) / ((uint64_t)dim * 4u)) / 256u * 256u);  // ~80 MB of fp32 rows
+        if (const char *cm = getenv("RG_KNN_CHUNK_MAX")) chunk_max = std::max<uint64_t>(256u, strtoull(cm, nullptr, 10) / 256u * 256u);
+    }
     uint32_t sort_n = 1;
     while (sort_n < cap + K) sort_n <<= 1;
     // query batches so that the candidate lists stay within ~2 GiB
@@ -783,7 +792,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
                 // still fit in L2 (tensor-core path without a seed: the re-rank gather of those ~3K survivors never reaches
                 // DRAM, and the fixed per-launch cost of filter + merge dominates there)
-                if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && lo < 65536) ? 3 * lo : lo, 1ull << 22);
+                if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && lo < 65536) ? 3 * lo : lo, chunk_max);
             }
             RG_CUDA(cudaGetLastError());
             uint32_t h_ovf = 0;

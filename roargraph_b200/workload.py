@@ -114,8 +114,11 @@ class SearchWorkload:
             rg.knn_release_workspace()
 
 
+BUILD_VERSION = 2  # bump when rg_index_build_roargraph's output changes (cached graphs of an older build must not be reused)
+
+
 def _cache_key(**kw) -> str:
-    s = repr(sorted(kw.items())) + f"abi{rg.lib().rg_abi_version()}"
+    s = repr(sorted(kw.items())) + f"abi{rg.lib().rg_abi_version()}build{BUILD_VERSION}"
     return hashlib.sha1(s.encode()).hexdigest()[:16]
 
 
