@@ -49,6 +49,8 @@ struct PruneParams {
     const uint32_t *knn;
     uint32_t knn_stride, M_sq;
     const int *owner;
+    uint32_t *qlist;      // mode 1: the pruned list of every training query (nsq x proj_stride)
+    int offers_by_query;  // mode 2: the offers' low word is a training-query index (the time of the push), not a node id
     uint32_t *proj, *supply;
     uint32_t proj_stride, supply_stride;
     const unsigned long long *in_keys;
@@ -201,9 +203,13 @@ __global__ void __launch_bounds__(kPruneThreads) prune_kernel(const PruneParams 
     __shared__ uint32_t s_n, s_pos_lo, s_more;
 
     const int tid = threadIdx.x;
-    const uint32_t v = p.node_lo + blockIdx.x;
+    const uint32_t v = p.mode == 1 ? p.knn[(size_t)blockIdx.x * p.knn_stride] : p.node_lo + blockIdx.x;
     const uint32_t dim4 = p.dim >> 2;
     const uint32_t M = p.M;
+    if (v >= p.nd) {  // a training query without a valid nearest base row
+        if (p.mode == 1 && tid == 0) p.qlist[(size_t)blockIdx.x * p.proj_stride] = 0;
+        return;
+    }
 
     if (p.mode == 2 || p.mode == 4) {
         // Reverse edges (ProjectionAddReverse :1394-1432, SupplyAddReverse :1352-1392) replayed in the reference's order: the
@@ -231,7 +237,17 @@ __global__ void __launch_bounds__(kPruneThreads) prune_kernel(const PruneParams 
             if (tid == 0) {  // append phase: offers in order, until the list is full and one more distinct source is waiting
                 uint32_t n = s_n, pos = s_pos_lo, more = 0;
                 while (pos < n_off) {
-                    const uint32_t src = (uint32_t)p.in_keys[ib + pos];
+                    uint32_t src = (uint32_t)p.in_keys[ib + pos];
+                    if (p.offers_by_query) {
+                        // phase 1 in the reference's order: training query `src` replaced its pivot's list and pushed the pivot
+                        // to the members of its pruned list at time `src`; a push that precedes the LAST replacement of v's own
+                        // list (v being the pivot of query owner[v]) was wiped by it (:1093)
+                        if ((int)src <= p.owner[v]) {
+                            ++pos;
+                            continue;
+                        }
+                        src = p.knn[(size_t)src * p.knn_stride];
+                    }
                     if (src == v || list_has(raw, n, src)) {
                         ++pos;
                         continue;
@@ -276,12 +292,13 @@ __global__ void __launch_bounds__(kPruneThreads) prune_kernel(const PruneParams 
     uint32_t target_cap = 0;
 
     if (p.mode == 1) {
-        const int o = p.owner[v];
-        if (o < 0) return;
+        // one CTA per TRAINING QUERY: its pivot's pruned list (PruneBiSearchBaseGetBase :1612-1694) depends on the query's
+        // kNN list alone, so every query's list is formed here; which one the pivot keeps (the last, :1093) and which pushes
+        // survive is replayed per destination in mode 2
         n = min(p.M_sq, kMaxCand);
-        for (uint32_t i = tid; i < n; i += kPruneThreads) raw[i] = p.knn[(size_t)o * p.knn_stride + i];
+        for (uint32_t i = tid; i < n; i += kPruneThreads) raw[i] = p.knn[(size_t)blockIdx.x * p.knn_stride + i];
         fill = true;
-        target = p.proj + (size_t)v * p.proj_stride;
+        target = p.qlist + (size_t)blockIdx.x * p.proj_stride;
         target_cap = M;
     } else if (p.mode == 3) {
         const uint32_t i0 = blockIdx.x;
@@ -328,6 +345,15 @@ __global__ void owner_kernel(const uint32_t *knn, uint32_t knn_stride, uint64_t 
     if (sq >= nsq) return;
     const uint32_t piv = knn[sq * knn_stride];
     if (piv < nd) atomicMax(owner + piv, (int)sq);  // "projection_graph_[cur_tgt] = pruned_list": the last writer wins
+}
+
+// projection_graph_[pivot] = the pruned list of the LAST training query that has this pivot (:1093)
+__global__ void owner_copy_kernel(const int *owner, const uint32_t *qlist, uint32_t *proj, uint32_t stride, uint64_t nd) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd * stride) return;
+    const uint64_t v = i / stride;
+    const int o = owner[v];
+    if (o >= 0) proj[i] = qlist[(uint64_t)o * stride + (i % stride)];
 }
 
 // keys (dst << 32 | src) for every edge of nodes [lo, lo + n); unused slots = ~0
@@ -495,7 +521,7 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
 
     Buf b_proj, b_supply, b_owner, b_keys_a, b_keys_b, b_cub, b_off, b_sum, b_best, b_exp_ids, b_exp_d, b_exp_cnt, b_out, b_maxdeg;
     int rc;
-    const uint64_t offer_slots = std::max<uint64_t>((uint64_t)nd * M, (uint64_t)batch * 2 * M);
+    const uint64_t offer_slots = std::max<uint64_t>(std::max<uint64_t>((uint64_t)nd * M, (uint64_t)nsq * M), (uint64_t)batch * 2 * M);
     size_t cub_bytes = 0;
     RG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                            offer_slots, 0, 64, s));
@@ -542,25 +568,52 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
     pp.supply_stride = sstride;
     pp.in_off = b_off.as<uint64_t>();
 
-    // phase 1a
+    static const bool trace = getenv("RG_BUILD_TRACE") != nullptr;  // per-phase degree totals (synchronises), to stderr
+    auto report = [&](const char *what, const uint32_t *adj, uint32_t stride) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        uint64_t nnz = 0;
+        if (adjacency_nnz_device(adj, stride, nd, &nnz) == RG_OK)
+            fprintf(stderr, "[rg build] %-46s total degree %llu, avg %.4f\n", what, (unsigned long long)nnz, (double)nnz / nd);
+    };
+    // phase 1a: every training query's pruned list; the pivot keeps the list of its last query
     RG_CUDA(cudaMemsetAsync(b_owner.p, 0xff, (size_t)nd * 4, s));
     owner_kernel<<<(unsigned)((nsq + 255) / 256), 256, 0, s>>>(d_knn, knn_stride, nsq, nd, b_owner.as<int>());
+    Buf b_qlist;
+    if ((rc = b_qlist.alloc((size_t)nsq * pstride * 4))) return rc;
+    pp.qlist = b_qlist.as<uint32_t>();
     pp.mode = 1;
     pp.node_lo = 0;
-    pp.n_nodes = nd;
-    prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
+    pp.n_nodes = (uint32_t)nsq;
+    prune_kernel<<<(unsigned)nsq, kPruneThreads, smem, s>>>(pp);
     RG_CUDA(cudaGetLastError());
-    // phase 1b, twice
+    owner_copy_kernel<<<(unsigned)(((uint64_t)nd * pstride + 255) / 256), 256, 0, s>>>(b_owner.as<int>(), pp.qlist, proj, pstride, nd);
+    report("projection, pivots pruned (1a)", proj, pstride);
+    // phase 1b: reverse edges.  Round 1 replays the pushes the reference makes right after every training query's prune
+    // (ProjectionAddReverse inside the loop, :1095): offers = (member of query sq's list) <- pivot(sq), in query order, those
+    // older than the destination's own last replacement dropped.  Round 2 = the pass over all nodes (:1105-1108).
     for (int round = 0; round < 2; ++round) {
         const unsigned long long *sorted = nullptr;
-        rc = gather_offers(proj, pstride, 0, nd, M, nd, b_keys_a.as<unsigned long long>(), b_keys_b.as<unsigned long long>(),
-                           b_cub.p, cub_bytes, b_off.as<uint64_t>(), &sorted, s);
+        if (round == 0)
+            rc = gather_offers(pp.qlist, pstride, 0, (uint32_t)nsq, M, nd, b_keys_a.as<unsigned long long>(),
+                               b_keys_b.as<unsigned long long>(), b_cub.p, cub_bytes, b_off.as<uint64_t>(), &sorted, s);
+        else
+            rc = gather_offers(proj, pstride, 0, nd, M, nd, b_keys_a.as<unsigned long long>(), b_keys_b.as<unsigned long long>(),
+                               b_cub.p, cub_bytes, b_off.as<uint64_t>(), &sorted, s);
         if (rc != RG_OK) return rc;
         pp.mode = 2;
+        pp.offers_by_query = round == 0 ? 1 : 0;
+        pp.node_lo = 0;
+        pp.n_nodes = nd;
         pp.in_keys = sorted;
         prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
         RG_CUDA(cudaGetLastError());
+        report(round == 0 ? "projection + reverse edges, round 1 (1b)" : "projection + reverse edges, round 2 (1b)", proj, pstride);
     }
+    pp.offers_by_query = 0;
+    RG_CUDA(cudaStreamSynchronize(s));
+    cudaFree(b_qlist.p);
+    b_qlist.p = nullptr;
     // supply graph starts as the projection graph (:1179-1184)
     copy_rows_kernel<<<(unsigned)(((uint64_t)nd * pstride + 255) / 256), 256, 0, s>>>(proj, pstride, supply, sstride, nd);
 
@@ -617,12 +670,14 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
         RG_CUDA(cudaGetLastError());
     }
+    report("supply graph after connectivity enhancement (3)", supply, sstride);
     // phase 4
     pp.mode = 5;
     pp.node_lo = 0;
     pp.n_nodes = nd;
     prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
     RG_CUDA(cudaGetLastError());
+    report("supply graph after the degree check (4)", supply, sstride);
     if ((rc = b_out.alloc((size_t)nd * ostride * 4))) return rc;
     RG_CUDA(cudaMemsetAsync(b_maxdeg.p, 0, 4, s));
     merge_rows_kernel<<<(nd + 255) / 256, 256, 0, s>>>(proj, pstride, supply, sstride, b_out.as<uint32_t>(), ostride, nd, M,

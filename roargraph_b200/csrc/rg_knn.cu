@@ -666,13 +666,12 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
     // the expected survivors per chunk stay near K
     const uint64_t n_seed = tc ? knn_tc_seed_rows(nb, K) : 0;
     const uint64_t chunk0 = tc ? 256u : cap;
-    // Largest chunk.  The re-rank after a chunk gathers fp32 rows of THAT chunk only, and a row is wanted by many queries of
-    // the batch (151 552 queries x ~K/8 survivors over ~10^5 rows: tens of reads per row), so a chunk whose fp32 rows fit in
-    // L2 turns the gather from HBM-bound into L2-bound — and tau tightens more often (fewer survivors overall).
-    // RG_KNN_CHUNK_MAX overrides (rows, rounded down to 256).
+    // Largest chunk.  Measured on a 10 M-row base (profiles/r2_knn_chunk_ab.txt): every filter + merge launch pair costs a
+    // fixed ~1.4 ms for a 151 552-query batch (one merge CTA per query), which outweighs what smaller chunks buy (tau
+    // tightening more often; the chunk's fp32 rows staying in L2 for the re-rank): 4 M rows 87 %, 262 144 rows 85 %,
+    // 104 704 rows 78 % of the sustained bf16 peak.  RG_KNN_CHUNK_MAX overrides (rows, rounded down to 256).
     uint64_t chunk_max = 1ull << 22;
     if (tc) {
-        chunk_max = std::max<uint64_t>(16384u, ((80ull << 20) / ((uint64_t)dim * 4u)) / 256u * 256u);  // ~80 MB of fp32 rows
         if (const char *cm = getenv("RG_KNN_CHUNK_MAX")) chunk_max = std::max<uint64_t>(256u, strtoull(cm, nullptr, 10) / 256u * 256u);
     }
     uint32_t sort_n = 1;

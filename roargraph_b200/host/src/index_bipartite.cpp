@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -104,12 +105,47 @@ void IndexBipartite::SetBaseData(const float *base, size_t n) {
   EnsureDeviceIndex();
 }
 
+// LoadVectorData (:2664-2695).  Single GPU: the base file streams straight into HBM (rg_index_create_from_fbin: 64 MB pinned
+// slabs, the copy of slab i overlapping the read of slab i + 1, rows padded to x8 by the copy engine, COSINE rows normalised
+// per slab by the reference's normalize on all host cores) — no 8-20 GB pageable host copy, GetBasePointSet() stays null.
+// Sharded (--gpus > 1) or RG_HOST_BASE=1: the rows are loaded to host memory first, as the reference does.
+static void normalize_hook(float *rows, uint64_t n, uint32_t dim, void *) { normalize_rows(rows, n, dim); }
+
 void IndexBipartite::LoadVectorData(const char *base_file, const char *sampled_query_file) {
   uint32_t base_num = 0, base_dim = 0, sq_num = 0, q_dim = 0;
   load_meta<float>(base_file, base_num, base_dim);
   if (strlen(sampled_query_file) != 0) {
     load_meta<float>(sampled_query_file, sq_num, q_dim);
     if (base_dim != q_dim) throw std::runtime_error("base and query dimension mismatch");
+  }
+  const char *host_base = getenv("RG_HOST_BASE");
+  if (gpus_ == 1 && !(host_base && host_base[0] == '1')) {
+    if ((base_dim + 7u) / 8u * 8u != dimension_)
+      throw std::runtime_error("base dimension (padded to x8) does not match the index dimension");
+    if (need_normalize) std::cout << "Normalizing base data" << std::endl;
+    if (dev_) {
+      rg_index_destroy(dev_);
+      dev_ = nullptr;
+    }
+    uint64_t nd = 0;
+    uint32_t pdim = 0;
+    int rc = rg_index_create_from_fbin(&dev_, base_file, to_rg_metric(metric_), need_normalize ? normalize_hook : nullptr, nullptr,
+                                       &nd, &pdim);
+    if (rc != RG_OK) {
+      const std::string msg = rg_last_error();
+      if (msg == "Data file size wrong!") {  // util.h:124
+        std::cerr << "Read file incompleted! filename:" << base_file << std::endl;
+        throw std::runtime_error(msg);
+      }
+      Fail(rc);
+    }
+    std::cout << "new_dim: " << pdim << std::endl;
+    free(owned_base_);
+    owned_base_ = nullptr;
+    data_bp_ = nullptr;
+    nd_ = nd;
+    nd_sq_ = sq_num;
+    return;
   }
   float *base = nullptr;
   load_data<float>(base_file, base_num, base_dim, base);
@@ -168,16 +204,38 @@ void IndexBipartite::LoadProjectionGraph(const char *filename) {
     }
     return;
   }
-  std::ifstream in(filename, std::ios::binary);
+  // one read of the whole file, decoded straight into CSR (10 M small vectors cost more than the search sweep); the host
+  // adjacency lists are materialised from the device copy only if GetProjectionGraph() is called
+  std::ifstream in(filename, std::ios::binary | std::ios::ate);
   if (!in.is_open()) throw std::runtime_error(std::string("cannot open index file ") + filename);
-  uint32_t npts = 0;
-  in.read((char *)&projection_ep_, 4);
+  const size_t fsize = (size_t)in.tellg();
+  if (fsize < 8 || fsize % 4) throw std::runtime_error("index file truncated");
+  std::vector<uint32_t> words(fsize / 4);
+  in.seekg(0, std::ios::beg);
+  in.read((char *)words.data(), (std::streamsize)fsize);
+  if (!in) throw std::runtime_error("index file truncated");
+  projection_ep_ = words[0];
+  const uint32_t npts = words[1];
   std::cout << "Projection graph, ep: " << projection_ep_ << std::endl;
-  in.read((char *)&npts, 4);
-  double deg = 0;
-  read_adjacency(in, npts, projection_graph_, deg);
-  std::cout << "Projection graph, avg_degree: " << deg / npts << std::endl;
-  UploadProjectionGraph();
+  if (npts != nd_) throw std::runtime_error("projection graph size does not match the base size");
+  std::vector<uint64_t> row_off((size_t)npts + 1, 0);
+  std::vector<uint32_t> nbrs;
+  nbrs.reserve(words.size() - 2 - npts);
+  size_t pos = 2;
+  for (uint32_t i = 0; i < npts; ++i) {
+    if (pos >= words.size()) throw std::runtime_error("index file truncated");
+    const uint32_t d = words[pos++];
+    if (pos + d > words.size()) throw std::runtime_error("index file truncated");
+    nbrs.insert(nbrs.end(), words.begin() + pos, words.begin() + pos + d);
+    pos += d;
+    row_off[i + 1] = nbrs.size();
+  }
+  std::cout << "Projection graph, avg_degree: " << (double)nbrs.size() / npts << std::endl;
+  EnsureDeviceIndex();
+  int rc = rg_index_set_graph(dev_, projection_ep_, row_off.data(), nbrs.data());
+  if (rc != RG_OK) Fail(rc);
+  projection_graph_.clear();
+  projection_host_valid_ = false;
 }
 
 IndexBipartite::CompactGraph &IndexBipartite::GetProjectionGraph() {
@@ -260,7 +318,7 @@ void IndexBipartite::Load(const char *filename) {
   double deg = 0;
   read_adjacency(in, npts, bipartite_graph_, deg);
   bipartite_uploaded_ = false;
-  if (data_bp_) UploadBipartiteGraph();
+  if (data_bp_ || dev_) UploadBipartiteGraph();
 }
 
 void IndexBipartite::UploadBipartiteGraph() {
@@ -479,7 +537,7 @@ void IndexBipartite::SearchBipartiteGraphBatch(const float *queries, size_t nq, 
                                                unsigned *indices, float *dists, uint32_t *cmps, uint32_t *hops) {
   const uint32_t L_pq = parameters.Get<uint32_t>("L_pq");
   std::lock_guard<std::mutex> guard(call_mutex_);
-  if (!bipartite_uploaded_ && !bipartite_graph_.empty() && data_bp_) UploadBipartiteGraph();
+  if (!bipartite_uploaded_ && !bipartite_graph_.empty() && (data_bp_ || dev_)) UploadBipartiteGraph();
   if (!dev_) throw std::runtime_error("index not loaded");
   std::vector<uint32_t> drawn;
   if (!init_ids) {

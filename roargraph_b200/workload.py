@@ -114,7 +114,7 @@ class SearchWorkload:
             rg.knn_release_workspace()
 
 
-BUILD_VERSION = 2  # bump when rg_index_build_roargraph's output changes (cached graphs of an older build must not be reused)
+BUILD_VERSION = 3  # bump when rg_index_build_roargraph's output changes (cached graphs of an older build must not be reused)
 
 
 def _cache_key(**kw) -> str:
