@@ -143,11 +143,11 @@ int knn_tc_convert(const float *x, uint64_t n, uint32_t dim, void *out_bf16, flo
 int knn_tc_max_norm(const float *sq, uint64_t n, float *d_out, cudaStream_t s);
 int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
                   int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
-                  uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s);
+                  uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s, uint32_t smem_reserve = 0);
 uint64_t knn_tc_seed_rows(uint64_t nb, uint32_t K);
 int knn_tc_seed(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t n_seed, uint32_t K,
                 int metric_l2, const float *qn, const float *bn, float bmax, float *seed_buf, float *tau, int sm_count,
-                cudaStream_t s);
+                cudaStream_t s, uint32_t smem_reserve = 0);
 
 // device time per phase of the kNN calls of this thread since the last reset (filled only under RG_KNN_TRACE=1)
 struct KnnProfile {

@@ -721,7 +721,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
     RG_WS(ws, top, WS_TOP, qb_alloc * K * sizeof(unsigned long long));
     RG_WS(ws, cand, WS_CAND, qb_alloc * cap * sizeof(unsigned long long));
     RG_WS(ws, cnt, WS_CNT, 2 * qb_alloc * sizeof(uint32_t));
-    RG_WS(ws, worklist, WS_WORK, (qb_alloc + 1) * sizeof(uint32_t));
+    RG_WS(ws, worklist, WS_WORK, (qb_alloc + 2) * sizeof(uint32_t));
     RG_WS(ws, tau, WS_TAU, qb_alloc * sizeof(float));
     RG_WS(ws, ovf, WS_OVF, sizeof(uint32_t));
     RG_CUDA(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
@@ -745,6 +745,29 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
             rr.queries = Q + qs * dim;
             rr.qn = qn + qs;
         }
+        // Two query lanes (tensor-core path, batches of at least two full waves, no tracing): the batch is split in halves A
+        // and B on two streams whose FILTER launches alternate (F(B,c) waits for F(A,c), F(A,c+1) for F(B,c)), so that the
+        // re-rank / merge of one half — an HBM gather that leaves the tensor cores idle — runs under the other half's filter.
+        // The filter leaves `reserve` bytes of shared memory per SM free so that merge CTAs fit beside its one CTA per SM.
+        const uint64_t pair_q = 256;
+        const uint64_t half = ((nqb / 2 + pair_q - 1) / pair_q) * pair_q;
+        static const bool two_lane_env = !(getenv("RG_KNN_LANES") && getenv("RG_KNN_LANES")[0] == '1');
+        const int n_lanes = (tc && !pt.on && two_lane_env && nqb >= 2ull * (uint64_t)sms * 256u && half < nqb) ? 2 : 1;
+        const uint32_t reserve = n_lanes == 2 ? 2u * (uint32_t)(fast_smem + 1536) : 0u;
+        cudaStream_t ls[2] = {s, s};
+        cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_init = nullptr;
+        if (n_lanes == 2) {
+            for (int l = 0; l < 2; ++l) {
+                RG_CUDA(cudaStreamCreateWithFlags(&ls[l], cudaStreamNonBlocking));
+                RG_CUDA(cudaEventCreateWithFlags(&ev_f[l], cudaEventDisableTiming));
+                RG_CUDA(cudaEventCreateWithFlags(&ev_done[l], cudaEventDisableTiming));
+            }
+            RG_CUDA(cudaEventCreateWithFlags(&ev_init, cudaEventDisableTiming));
+        }
+        struct Lane { uint64_t off, n; };
+        const Lane lanes[2] = {{0, n_lanes == 2 ? half : nqb}, {half, nqb - half}};
+        const uint32_t kp16 = tc ? knn_tc_pitch(dim) : 0;
+        int rc_lane = RG_OK;
         for (int attempt = 0; attempt < 2; ++attempt) {
             // attempt 0: seeded tau (or tau = inf and a 256-row first chunk), chunks growing with the rows seen (expected
             // survivors per chunk ~K); attempt 1 (after a candidate-list overflow): every chunk has at most `cap` rows,
@@ -752,40 +775,66 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
             const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
             knn_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, s>>>(top, nqb * K, tau, cnt, nqb);
             RG_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), s));
+            if (n_lanes == 2) {
+                RG_CUDA(cudaEventRecord(ev_init, s));
+                for (int l = 0; l < 2; ++l) RG_CUDA(cudaStreamWaitEvent(ls[l], ev_init, 0));
+            }
             const bool seeded = attempt == 0 && n_seed != 0;
             if (seeded) {
                 pt.begin();
-                int rc = knn_tc_seed(q16, nqb, kb->b16, nb, dim, n_seed, K, metric_l2, qn + qs, kb->bn, kb->bmax, seed_buf, tau, sms, s);
-                if (rc != RG_OK) return rc;
+                for (int l = 0; l < n_lanes; ++l) {
+                    const Lane &ln = lanes[l];
+                    int rc = knn_tc_seed((const char *)q16 + ln.off * kp16 * 2, ln.n, kb->b16, nb, dim, n_seed, K, metric_l2,
+                                         qn + qs + ln.off, kb->bn, kb->bmax, seed_buf + (n_seed / 128u) * ln.off, tau + ln.off, sms, ls[l],
+                                         reserve);
+                    if (rc != RG_OK) return rc;
+                }
                 pt.end(t_profile.seed_ms);
             }
             uint64_t lo = 0;
             uint64_t csize = attempt == 1 ? (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap) : (seeded ? n_seed : chunk0);
+            bool first_filter = true;
             while (lo < nb) {
                 const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
-                pt.begin();
-                if (tc) {
-                    int rc = knn_tc_filter(q16, nqb, kb->b16, nb, dim, lo, hi, metric_l2, tau, qn + qs, kb->bn, kb->bmax, cand, cnt, cap,
-                                           ovf, sms, s);
-                    if (rc != RG_OK) return rc;
-                } else {
-                    dim3 grid((unsigned)((hi - lo + TB - 1) / TB), (unsigned)((nqb + TQ - 1) / TQ));
-                    knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, kb->B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
-                                                                        kb->bn, metric_l2, tau, cand, cnt, cap, ovf);
+                for (int l = 0; l < n_lanes; ++l) {
+                    const Lane &ln = lanes[l];
+                    cudaStream_t st = ls[l];
+                    unsigned long long *l_top = top + ln.off * K, *l_cand = cand + ln.off * cap;
+                    uint32_t *l_cnt = cnt + 2 * ln.off, *l_work = worklist + ln.off, *l_work_cnt = work_cnt + l;
+                    float *l_tau = tau + ln.off;
+                    Rerank lr = rr;
+                    if (tc) {
+                        lr.queries = rr.queries + ln.off * dim;
+                        lr.qn = rr.qn + ln.off;
+                    }
+                    pt.begin();
+                    if (tc) {
+                        // the other lane's latest filter has finished: the two filters never share the tensor cores
+                        if (n_lanes == 2 && !first_filter) RG_CUDA(cudaStreamWaitEvent(st, ev_f[1 - l], 0));
+                        int rc = knn_tc_filter((const char *)q16 + ln.off * kp16 * 2, ln.n, kb->b16, nb, dim, lo, hi, metric_l2, l_tau,
+                                               qn + qs + ln.off, kb->bn, kb->bmax, l_cand, l_cnt, cap, ovf, sms, st, reserve);
+                        if (rc != RG_OK) return rc;
+                        if (n_lanes == 2) RG_CUDA(cudaEventRecord(ev_f[l], st));
+                        first_filter = false;
+                    } else {
+                        dim3 grid((unsigned)((hi - lo + TB - 1) / TB), (unsigned)((nqb + TQ - 1) / TQ));
+                        knn_gemm_filter_kernel<<<grid, KNN_THREADS, 0, s>>>(Q + qs * dim, kb->B, dim, nqb, lo, hi, qn ? qn + qs : nullptr,
+                                                                            kb->bn, metric_l2, tau, cand, cnt, cap, ovf);
+                    }
+                    pt.end(t_profile.filter_ms);
+                    pt.begin();
+                    if (tc) {
+                        // fast path per query, then the general kernel over the (normally empty) work list of long lists
+                        RG_CUDA(cudaMemsetAsync(l_work_cnt, 0, sizeof(uint32_t), st));
+                        if (vec) knn_merge_fast_kernel<true><<<(unsigned)ln.n, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt);
+                        else knn_merge_fast_kernel<false><<<(unsigned)ln.n, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt);
+                        knn_merge_kernel<<<(unsigned)std::min<uint64_t>(ln.n, 2ull * sms), 256, merge_smem, st>>>(
+                            l_top, K, l_cand, l_cnt, cap, l_tau, sort_n, lr, l_work, l_work_cnt);
+                    } else {
+                        knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr, nullptr, nullptr);
+                    }
+                    pt.end(t_profile.merge_ms);
                 }
-                pt.end(t_profile.filter_ms);
-                pt.begin();
-                if (tc) {
-                    // fast path per query, then the general kernel over the (normally empty) work list of long lists
-                    RG_CUDA(cudaMemsetAsync(work_cnt, 0, sizeof(uint32_t), s));
-                    if (vec) knn_merge_fast_kernel<true><<<(unsigned)nqb, 128, fast_smem, s>>>(top, K, cand, cnt, cap, tau, fast_sn, rr, worklist, work_cnt);
-                    else knn_merge_fast_kernel<false><<<(unsigned)nqb, 128, fast_smem, s>>>(top, K, cand, cnt, cap, tau, fast_sn, rr, worklist, work_cnt);
-                    knn_merge_kernel<<<(unsigned)std::min<uint64_t>(nqb, 2ull * sms), 256, merge_smem, s>>>(
-                        top, K, cand, cnt, cap, tau, sort_n, rr, worklist, work_cnt);
-                } else {
-                    knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr, nullptr, nullptr);
-                }
-                pt.end(t_profile.merge_ms);
                 t_profile.chunks += 1;
                 lo = hi;
                 // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
@@ -793,14 +842,29 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 // DRAM, and the fixed per-launch cost of filter + merge dominates there)
                 if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && lo < 65536) ? 3 * lo : lo, chunk_max);
             }
-            RG_CUDA(cudaGetLastError());
+            rc_lane = cudaGetLastError() == cudaSuccess ? RG_OK : RG_ECUDA;
+            if (n_lanes == 2)
+                for (int l = 0; l < 2; ++l) {
+                    RG_CUDA(cudaEventRecord(ev_done[l], ls[l]));
+                    RG_CUDA(cudaStreamWaitEvent(s, ev_done[l], 0));
+                }
             uint32_t h_ovf = 0;
             RG_CUDA(cudaMemcpyAsync(&h_ovf, ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             RG_CUDA(cudaStreamSynchronize(s));
+            if (rc_lane != RG_OK) { set_error("rg_knn: kernel launch failed"); break; }
             if (!h_ovf) break;
             t_profile.overflow_retries += 1;
-            if (attempt == 1) { set_error("rg_knn: candidate overflow in safe mode (internal error)"); return RG_ENOMEM; }
+            if (attempt == 1) { set_error("rg_knn: candidate overflow in safe mode (internal error)"); rc_lane = RG_ENOMEM; break; }
         }
+        if (n_lanes == 2) {
+            for (int l = 0; l < 2; ++l) {
+                cudaStreamDestroy(ls[l]);
+                cudaEventDestroy(ev_f[l]);
+                cudaEventDestroy(ev_done[l]);
+            }
+            cudaEventDestroy(ev_init);
+        }
+        if (rc_lane != RG_OK) return rc_lane;
         knn_unpack_kernel<<<(unsigned)((nqb * K + 255) / 256), 256, 0, s>>>(top, nqb * K, id_offset, d_ids + qs * K, d_dists + qs * K);
     }
     RG_CUDA(cudaGetLastError());

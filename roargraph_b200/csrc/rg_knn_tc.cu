@@ -243,6 +243,7 @@ struct TcParams {
     // of each tile, seed_out[((tile - tile_lo) * 2 + half) * seed_stride + query]
     float *seed_out;
     uint64_t seed_stride;
+    uint32_t smem_reserve;  // shared memory per SM left free for the merge CTAs of the other query lane (rg_knn.cu)
 };
 
 // NQT = query tiles per CTA.  NQT == 2 (dim <= 256): 256 queries share every base tile, which halves the L2 -> SM operand
@@ -814,7 +815,8 @@ static int launch_filter_pair(const void *q_bf16, uint64_t nq, const void *b_bf1
     rc = make_map(&map_b, b_bf16, nb, kp, kPairN / 2);
     if (rc != RG_OK) return rc;
     const size_t fixed = (size_t)p.num_kb * kABytesPerKb + 2 * kPairN * 4 + 512 + 1024;
-    const size_t budget = 227 * 1024;
+    size_t budget = 227 * 1024;
+    if (p.smem_reserve && fixed + 4 * kPairBBytesPerKb + p.smem_reserve <= budget) budget -= p.smem_reserve;  // never below 4 stages
     uint32_t stages = (uint32_t)((budget - fixed) / kPairBBytesPerKb);
     if (stages > 12) stages = 12;
     p.stages = stages;
@@ -903,7 +905,7 @@ __global__ void __launch_bounds__(256) knn_seed_select_kernel(const float *__res
 // over those rows, from the tensor-core scores alone (no candidate lists, no re-rank).  seed_buf: 2 * n_seed / 256 * nq floats.
 int knn_tc_seed(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t n_seed, uint32_t K,
                 int metric_l2, const float *qn, const float *bn, float bmax, float *seed_buf, float *tau, int sm_count,
-                cudaStream_t s) {
+                cudaStream_t s, uint32_t smem_reserve) {
     const uint32_t kp = knn_tc_pitch(dim);
     const uint32_t G = (uint32_t)(n_seed / 128u);
     if (n_seed == 0 || n_seed % 256u != 0 || n_seed > nb || G < K || G > 32u * kSeedMaxPerLane) {
@@ -923,6 +925,7 @@ int knn_tc_seed(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb
     p.err_rel = kErrRel;
     p.seed_out = seed_buf;
     p.seed_stride = nq;
+    p.smem_reserve = smem_reserve;
     int rc = launch_filter_pair(q_bf16, nq, b_bf16, nb, kp, 0, n_seed, p, sm_count, s);
     if (rc != RG_OK) return rc;
     const size_t smem = (size_t)G * 33u * sizeof(float);
@@ -946,9 +949,10 @@ uint64_t knn_tc_seed_rows(uint64_t nb, uint32_t K) {
 
 int knn_tc_filter(const void *q_bf16, uint64_t nq, const void *b_bf16, uint64_t nb, uint32_t dim, uint64_t row_lo, uint64_t row_hi,
                   int metric_l2, const float *tau, const float *qn, const float *bn, float bmax, unsigned long long *cand,
-                  uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s) {
+                  uint32_t *cand_cnt, uint32_t cap, uint32_t *overflow, int sm_count, cudaStream_t s, uint32_t smem_reserve) {
     const uint32_t kp = knn_tc_pitch(dim);
     TcParams p{};
+    p.smem_reserve = smem_reserve;
     p.nq = nq;
     p.nb = nb;
     p.num_kb = (kp + kBlockK - 1) / kBlockK;
