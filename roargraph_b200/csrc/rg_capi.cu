@@ -577,6 +577,7 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
         // doubles as the adjacency-prefetch switch; off by default: at 24 resident warps per SM the extra L2 fills cost
         // more DRAM bandwidth than the shorter dependent read saves (profiles/r1_tune_10M.csv)
         p.n_init = (pf && pf[0] == '1') ? 1u : (pf && pf[0] == '2') ? 2u : 0u;  // 1: on queue insertion, 2: the next-best node at hop start
+        p.drop_ep = 1;  // SearchRoarGraph does not mark its entry point visited (src/index_bipartite.cpp:2349 is commented out)
     }
     p.queries = d_q;
     p.out_ids = d_ids;

@@ -50,6 +50,9 @@ struct SearchParams {
     uint32_t row_stride_smem; // floats; == dim padded so that (stride % 32) == 16 (bank-conflict-free float4 reads)
     uint32_t warp_smem_bytes; // bytes of dynamic smem per warp
     int metric_l2;            // 1: squared L2, 0: negative inner product
+    uint32_t cand_words;      // candidate-id scratch per warp (words)
+    uint32_t lazy_queue;      // 1: long queue kept as sorted arrays + a pending block flushed every ~30 accepted candidates
+    uint32_t drop_ep;         // 1: SearchRoarGraph — the entry point is not marked visited and may be evaluated again (9.1)
     uint32_t merge_insert;    // 1: the candidates of a row group enter the queue in one merge pass (RG_QUEUE_MERGE, default 1)
     // L2-resident exact visited set (SearchRoarGraph only; see rg_search.cu "visited table"): per slot 2^vt_bbits buckets
     // of 16 x 16-bit entries; 0 = use the tag arrays

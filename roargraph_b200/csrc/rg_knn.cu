@@ -272,16 +272,19 @@ __global__ void __launch_bounds__(128) knn_merge_fast_kernel(unsigned long long 
                                                              const unsigned long long *__restrict__ cand,
                                                              uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau,
                                                              uint32_t sn, const Rerank rr, uint32_t *__restrict__ worklist,
-                                                             uint32_t *__restrict__ work_cnt) {
+                                                             uint32_t *__restrict__ work_cnt, uint64_t nq) {
     extern __shared__ unsigned long long sk[];
     __shared__ uint32_t s_kept;
-    const uint64_t q = blockIdx.x;
+    // grid-stride over the queries: one CTA per query when the grid is nq, or a small persistent grid (two CTAs per SM) when
+    // this merge has to fit beside the other query lane's filter CTA (rg_knn.cu, two query lanes)
+    for (uint64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    __syncthreads();  // the previous query's sort buffer and s_kept are no longer read
     const CandList cl(cand_cnt, q, cap);
     const uint32_t n = cl.size();
-    if (n == 0) return;
+    if (n == 0) continue;
     if (n + K > sn) {
         if (threadIdx.x == 0) worklist[atomicAdd(work_cnt, 1u)] = (uint32_t)q;
-        return;
+        continue;
     }
     float *sq = reinterpret_cast<float *>(sk + sn);
     if (VEC) {
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(128) knn_merge_fast_kernel(unsigned long long 
         cand_cnt[2 * q] = 0;
         cand_cnt[2 * q + 1] = 0;
     }
+    }  // query loop
 }
 
 __global__ void knn_init_kernel(unsigned long long *top, uint64_t n_top, float *tau, uint32_t *cnt, uint64_t nq) {
@@ -826,9 +830,14 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                     if (tc) {
                         // fast path per query, then the general kernel over the (normally empty) work list of long lists
                         RG_CUDA(cudaMemsetAsync(l_work_cnt, 0, sizeof(uint32_t), st));
-                        if (vec) knn_merge_fast_kernel<true><<<(unsigned)ln.n, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt);
-                        else knn_merge_fast_kernel<false><<<(unsigned)ln.n, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt);
-                        knn_merge_kernel<<<(unsigned)std::min<uint64_t>(ln.n, 2ull * sms), 256, merge_smem, st>>>(
+                        // two lanes: a persistent grid of two CTAs per SM, which fits beside the other lane's filter CTA (one CTA per
+                        // query would flood every SM's shared memory and keep the 195 KB filter CTAs out until the merge is over)
+                        const unsigned mgrid = n_lanes == 2 ? (unsigned)std::min<uint64_t>(ln.n, 2ull * sms) : (unsigned)ln.n;
+                        if (vec) knn_merge_fast_kernel<true><<<mgrid, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt, ln.n);
+                        else knn_merge_fast_kernel<false><<<mgrid, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt, ln.n);
+                        // (two lanes: a handful of CTAs — its 34 KB sort buffer does not fit beside a filter CTA, and the list is
+                        // normally empty)
+                        knn_merge_kernel<<<(unsigned)std::min<uint64_t>(ln.n, n_lanes == 2 ? 16ull : 2ull * sms), 256, merge_smem, st>>>(
                             l_top, K, l_cand, l_cnt, cap, l_tau, sort_n, lr, l_work, l_work_cnt);
                     } else {
                         knn_merge_kernel<<<(unsigned)nqb, 256, merge_smem, s>>>(top, K, cand, cnt, cap, tau, sort_n, rr, nullptr, nullptr);

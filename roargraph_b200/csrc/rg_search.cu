@@ -162,7 +162,14 @@ struct WarpCtx {
     uint32_t size, cur, phase;
     uint64_t row_policy;  // L2 eviction policy of the row copies (0 = none)
     int lane;
+    // lazy queue (long queues): accepted candidates wait here, unsorted, and enter the sorted arrays kPendMax at a time
+    float *pd;           // kPendSlots distances
+    uint32_t *pi;        // kPendSlots ids | kExpandedBit
+    uint32_t npend, npu; // entries waiting / of them not yet expanded
 };
+
+constexpr uint32_t kPendSlots = 32;
+constexpr uint32_t kPendMax = 31;  // lane 31 of the sorted pending block stays a sentinel (32-entry search by shuffles)
 
 // NeighborPriorityQueue::insert (neighbor.h:150-183), warp-cooperative.  All lanes pass the same (cd, cid).
 // Returns true when the candidate entered the queue.
@@ -359,6 +366,215 @@ __device__ __forceinline__ uint32_t queue_pop(WarpCtx &w, float *dist_out = null
     return u;
 }
 
+// ---- lazy queue (L_pq >= RG_LAZY_QUEUE_MIN_L) ------------------------------------------------------------------------------
+// With a long queue the O(L / 32) shift of every insert pass is most of a hop.  The lazy form keeps NeighborPriorityQueue's
+// sorted arrays ("main") plus up to kPendMax accepted candidates in an unsorted pending block, and pays the shift once per
+// ~30 accepted candidates.  It stays observably identical to the reference's eager queue Q* (the L best (distance, id) of
+// everything seen, neighbor.h:150-192):
+//   * a candidate is accepted iff it beats main's last entry when main is full — a superset of what Q* accepts, because
+//     Q* is the L best of main + pending and its worst is therefore no worse than main's; what Q* would have dropped falls
+//     off the end at the next flush;
+//   * closest_unexpanded = the smaller of main[cur] and the best unexpanded pending entry.  It is the best unexpanded entry
+//     seen, so it is the one the reference expands next — provided it lies inside Q*, i.e. fewer than L entries are better:
+//     its rank = (entries of main before it) + (pending entries before it, all already expanded); at rank >= L the reference
+//     has no unexpanded entry left inside its queue and stops, and so does this;
+//   * an expanded pending entry keeps its flag through the flush, entries never re-enter, and the only id that
+//     can be evaluated twice — the entry point, which SearchRoarGraph does not mark visited (9.1) — is always rejected by the
+//     reference (exact duplicate, or worse than a worst entry that only improves) and is dropped here.
+
+// number of main entries e with !(c < e): the upper bound NeighborPriorityQueue::insert computes (neighbor.h:155-167)
+__device__ __forceinline__ uint32_t queue_upper_bound(const WarpCtx &w, float cd, uint32_t cid) {
+    const int lane = w.lane;
+    const float *qd = w.qd;
+    const uint32_t *qi = w.qi;
+    uint32_t lo = 0, len = w.size;
+    while (len > 32) {
+        const uint32_t step = (len + 31) >> 5;
+        const uint32_t end = lo + len;
+        const uint32_t idx = min(lo + (lane + 1) * step, end) - 1;
+        const bool le = !nbr_less(cd, cid, qd[idx], qi[idx] & kIdMask);
+        const uint32_t nle = __popc(__ballot_sync(kFull, le));
+        if (nle == 32) {
+            lo = end;
+            len = 0;
+        } else {
+            const uint32_t new_lo = (nle == 0) ? lo : min(lo + nle * step, end);
+            const uint32_t p_hi = min(lo + (nle + 1) * step, end) - 1;
+            lo = new_lo;
+            len = p_hi - new_lo;
+        }
+    }
+    bool le = false;
+    if ((uint32_t)lane < len) le = !nbr_less(cd, cid, qd[lo + lane], qi[lo + lane] & kIdMask);
+    return lo + __popc(__ballot_sync(kFull, le));
+}
+
+// pending block -> main: sort the block across the lanes, move every main entry up by the number of pending entries that
+// precede it (top chunk first, in place), drop the pending entries in, cut at L, recompute the cursor
+__device__ __forceinline__ void queue_flush(WarpCtx &w, uint32_t L) {
+    const uint32_t np = w.npend;
+    if (!np) return;
+    const int lane = w.lane;
+    float *qd = w.qd;
+    uint32_t *qi = w.qi;
+    float d = (uint32_t)lane < np ? w.pd[lane] : INFINITY;
+    uint32_t iw = (uint32_t)lane < np ? w.pi[lane] : kIdMask;  // sentinel: (+inf, largest id) sorts behind everything
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float od = __shfl_xor_sync(kFull, d, j);
+            const uint32_t oi = __shfl_xor_sync(kFull, iw, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            const bool other_less = nbr_less(od, oi & kIdMask, d, iw & kIdMask);
+            const bool mine_less = nbr_less(d, iw & kIdMask, od, oi & kIdMask);
+            const bool take = (lower == up) ? other_less : mine_less;  // keep the smaller / the larger of the pair
+            if (take) {
+                d = od;
+                iw = oi;
+            }
+        }
+    }
+    // lane r < np now holds the r-th smallest pending entry; lanes >= np hold sentinels
+    const uint32_t size = w.size;
+    // pending entries preceding a key (the block is sorted: a 5-step search over the lanes)
+    auto pend_before = [&](float ed, uint32_t ei) -> uint32_t {
+        uint32_t c = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const float pdv = __shfl_sync(kFull, d, c + step - 1);
+            const uint32_t piv = __shfl_sync(kFull, iw, c + step - 1);
+            if (nbr_less(pdv, piv & kIdMask, ed, ei)) c += step;
+        }
+        return c;  // <= 31: lane 31 is a sentinel (np <= kPendMax)
+    };
+    // where the old cursor entry goes
+    uint32_t cur_new = 0xffffffffu;
+    if (w.cur < size) cur_new = w.cur + pend_before(qd[w.cur], qi[w.cur] & kIdMask);
+    else (void)pend_before(0.f, 0u);  // keep the shuffles convergent
+    // upper bound of every pending entry in main: one cooperative 32-ary search per entry would serialise, so each lane
+    // runs its own binary search (np <= 31 searches in parallel)
+    uint32_t ub = 0;
+    {
+        uint32_t lo = 0, hi = (uint32_t)lane < np ? size : 0u;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (nbr_less(d, iw & kIdMask, qd[mid], qi[mid] & kIdMask)) hi = mid;
+            else lo = mid + 1;
+        }
+        ub = lo;
+    }
+    const uint32_t minpos = __shfl_sync(kFull, ub, 0);
+    for (int top = (int)size - 1; top >= (int)minpos; top -= 32) {
+        const int j = top - lane;
+        const bool act = j >= (int)minpos;
+        const float ed = act ? qd[j] : 0.f;
+        const uint32_t ew = act ? qi[j] : 0u;
+        const uint32_t nj = (uint32_t)j + pend_before(ed, ew & kIdMask);
+        __syncwarp();
+        if (act && nj < L) {
+            qd[nj] = ed;
+            qi[nj] = ew;
+        }
+        __syncwarp();
+    }
+    const uint32_t fin = ub + (uint32_t)lane;
+    const bool placed = (uint32_t)lane < np && fin < L;
+    if (placed) {
+        qd[fin] = d;
+        qi[fin] = iw;  // an entry expanded while it was pending keeps its flag
+    }
+    __syncwarp();
+    const uint32_t newsize = min(size + np, L);
+    // first unexpanded entry: the old cursor entry at its new place, or the first unexpanded newcomer
+    uint32_t first = placed && !(iw & kExpandedBit) ? fin : 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(kFull, first, o));
+    w.cur = min(min(cur_new, first), newsize);
+    w.size = newsize;
+    w.npend = 0;
+    w.npu = 0;
+}
+
+// up to 8 accepted candidates of a row group (lanes with `pass`) join the pending block
+__device__ __forceinline__ void pending_append(WarpCtx &w, const SearchParams &p, float d, uint32_t id, bool pass, bool drop_ep) {
+    if (drop_ep && id == p.ep) pass = false;  // the entry point evaluated again: the reference's queue always rejects it
+    uint32_t m = __ballot_sync(kFull, pass);
+    if (!m) return;
+    if (w.npend + (uint32_t)__popc(m) > kPendMax) {
+        queue_flush(w, p.L);
+        if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
+        m = __ballot_sync(kFull, pass);
+        if (!m) return;
+    }
+    if (pass) {
+        const uint32_t slot = w.npend + __popc(m & ((1u << w.lane) - 1u));
+        w.pd[slot] = d;
+        w.pi[slot] = id;
+    }
+    __syncwarp();
+    w.npend += __popc(m);
+    w.npu += __popc(m);
+}
+
+// closest_unexpanded over main + pending; 0xffffffff = no unexpanded entry inside the reference's top L
+__device__ __forceinline__ uint32_t queue_pop_lazy(WarpCtx &w, uint32_t L, float *dist_out) {
+    const int lane = w.lane;
+    const bool hasA = w.cur < w.size;
+    const float ad = hasA ? w.qd[w.cur] : INFINITY;
+    const uint32_t ai = hasA ? (w.qi[w.cur] & kIdMask) : kIdMask;
+    // best unexpanded pending entry
+    const bool mine = (uint32_t)lane < w.npend && !(w.pi[lane] & kExpandedBit);
+    const float md = mine ? w.pd[lane] : INFINITY;
+    const uint32_t mi = mine ? w.pi[lane] : kIdMask;
+    float bd = md;
+    uint32_t bi = mi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(kFull, bd, o);
+        const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
+        if (nbr_less(od, oi, bd, bi)) {
+            bd = od;
+            bi = oi;
+        }
+    }
+    const bool hasB = w.npu != 0;
+    if (!hasA && !hasB) return 0xffffffffu;
+    const bool useB = hasB && (!hasA || nbr_less(bd, bi, ad, ai));
+    const float ud = useB ? bd : ad;
+    const uint32_t ui = useB ? bi : ai;
+    if (w.size + w.npend > L) {
+        // the queue may hold more than L entries: is this one inside the L best?  (everything better is already expanded)
+        const bool before = (uint32_t)lane < w.npend && nbr_less(w.pd[lane], w.pi[lane] & kIdMask, ud, ui);
+        const uint32_t cntp = __popc(__ballot_sync(kFull, before));
+        const uint32_t posm = useB ? queue_upper_bound(w, ud, ui) : w.cur;
+        if (posm + cntp >= L) return 0xffffffffu;
+    }
+    if (dist_out) *dist_out = ud;
+    __syncwarp();
+    if (useB) {
+        if (mine && mi == ui) w.pi[lane] = ui | kExpandedBit;
+        __syncwarp();
+        --w.npu;
+    } else {
+        if (lane == 0) w.qi[w.cur] = ui | kExpandedBit;
+        __syncwarp();
+        uint32_t c = w.cur + 1;
+        for (;;) {
+            const uint32_t j = c + lane;
+            const bool stop = (j >= w.size) || !(w.qi[j] & kExpandedBit);
+            const uint32_t mm = __ballot_sync(kFull, stop);
+            if (mm) {
+                c += __ffs(mm) - 1;
+                break;
+            }
+            c += 32;
+        }
+        w.cur = min(c, w.size);
+    }
+    return ui;
+}
+
 // Evaluate cand[0..n) against the query and insert them: gather rows with bulk copies, 8 rows per mbarrier group.
 template <bool kL2>
 __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchParams &p, uint32_t n, bool prefetch_adj,
@@ -388,7 +604,8 @@ __device__ __forceinline__ void evaluate_candidates(WarpCtx &w, const SearchPara
             const uint32_t id = valid ? w.cand[b0 + r] : 0u;
             bool pass = valid && t == 0;
             if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
-            if (prefetch_adj) queue_insert_group<true>(w, p, d, id, pass, unique_ids);
+            if (p.lazy_queue && unique_ids) pending_append(w, p, d, id, pass, p.drop_ep != 0);
+            else if (prefetch_adj) queue_insert_group<true>(w, p, d, id, pass, unique_ids);
             else queue_insert_group<false>(w, p, d, id, pass, unique_ids);
         }
         __syncwarp();
@@ -433,7 +650,8 @@ __device__ __forceinline__ void evaluate_candidates_db(WarpCtx &w, const SearchP
         if (g + 2 < ngroups) issue(g + 2);
         bool pass = valid && t == 0;
         if (pass && w.size == p.L) pass = nbr_less(d, id, w.qd[p.L - 1], w.qi[p.L - 1] & kIdMask);
-        if (prefetch_adj) queue_insert_group<true>(w, p, d, id, pass, unique_ids);
+        if (p.lazy_queue && unique_ids) pending_append(w, p, d, id, pass, p.drop_ep != 0);
+        else if (prefetch_adj) queue_insert_group<true>(w, p, d, id, pass, unique_ids);
         else queue_insert_group<false>(w, p, d, id, pass, unique_ids);
     }
     __syncwarp();
@@ -594,6 +812,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
     w.qd = w.rows + (size_t)p.rows_per_batch * p.row_stride_smem;
     w.qi = reinterpret_cast<uint32_t *>(w.qd + p.L);
     w.cand = w.qi + p.L;
+    w.pd = reinterpret_cast<float *>(w.cand + p.cand_words);  // kPendSlots floats + kPendSlots ids, only when lazy_queue
+    w.pi = reinterpret_cast<uint32_t *>(w.pd + kPendSlots);
     w.bar0 = smem_u32(bars);
     w.rows_u32 = smem_u32(w.rows);
     w.phase = 0;
@@ -610,7 +830,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
     const bool vt_smem = use_vt && p.vt_smem;
     uint32_t *vt = nullptr;
     if (use_vt) {
-        if (vt_smem) vt = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(w.cand + kCandCap) + 31u) & ~(uintptr_t)31u);
+        if (vt_smem) vt = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(w.cand + p.cand_words + (p.lazy_queue ? 2u * kPendSlots : 0u)) + 31u) & ~(uintptr_t)31u);
         else vt = p.vtab + (size_t)slot * p.vt_words;
     }
     w.row_policy = (use_vt && !vt_smem) ? policy_evict_first() : 0ull;
@@ -673,6 +893,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
         }
         w.size = 0;
         w.cur = 0;
+        w.npend = 0;
+        w.npu = 0;
         __syncwarp();
 
         uint32_t cmps = 0, hops = 0, adjw = 0;
@@ -683,7 +905,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
                 if (kBuild) __stcg(tags + p.ep, (uint8_t)epoch);  // :1307 the build's search does mark it
             }
             __syncwarp();
-            evaluate<kL2>(w, p, 1, false);
+            evaluate<kL2>(w, p, 1, false, /*unique_ids=*/false);  // straight into the (empty) sorted arrays, lazy queue or not
         } else {
             for (uint32_t i = lane; i < p.n_init; i += 32) {
                 uint32_t id;
@@ -696,9 +918,15 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
             evaluate<kL2>(w, p, p.n_init, false, /*unique_ids=*/false);  // random entry points may repeat
         }
 
-        while (w.cur < w.size) {  // has_unexpanded_node
+        while (w.cur < w.size || w.npu) {  // has_unexpanded_node
             float ud;
-            const uint32_t u = queue_pop(w, kBuild ? &ud : nullptr);
+            uint32_t u;
+            if (p.lazy_queue) {
+                u = queue_pop_lazy(w, p.L, kBuild ? &ud : nullptr);
+                if (u == 0xffffffffu) break;  // nothing unexpanded inside the L best
+            } else {
+                u = queue_pop(w, kBuild ? &ud : nullptr);
+            }
             if (kBuild && lane == 0 && hops < p.exp_cap) {  // full_retset.push_back(cur_check_node) :1316
                 p.exp_ids[(size_t)qidx * p.exp_cap + hops] = u;
                 p.exp_dists[(size_t)qidx * p.exp_cap + hops] = ud;
@@ -784,6 +1012,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) beam_search_kernel(const Sear
             }
         }
 
+        if (p.lazy_queue) queue_flush(w, p.L);
         if (kBuild) {
             if (lane == 0) p.exp_cnt[qidx] = min(hops, p.exp_cap);
         } else {
@@ -853,6 +1082,7 @@ uint32_t env_u32(const char *name, uint32_t dflt) {
 constexpr uint32_t kMaxSmemPerCta = 227u * 1024u;
 
 uint32_t warp_smem_bytes(uint32_t dim, uint32_t rstride, uint32_t R, uint32_t L, uint32_t vt_bytes = 0, uint32_t cand_words = kCandCap) {
+    // cand_words carries the pending block of the lazy queue too (plan_search adds 2 * kPendSlots words)
     uint32_t b = 64 + dim * 4 + R * rstride * 4 + L * 8 + cand_words * 4;
     if (vt_bytes) b += 32 + vt_bytes;  // the shared-memory visited table, 32-byte aligned behind the candidate ids
     return (b + 127u) & ~127u;
@@ -931,7 +1161,14 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
     const uint32_t vt_bytes = p.vt_smem ? p.vt_words * 4u : 0u;
     // candidate-id scratch per warp: one 96-id pass; the bipartite search (row_off set) gathers the fresh ids of several
     // passes before it evaluates them, so that whole 8-row groups go through the row ring
-    const uint32_t cw = p.row_off ? 2u * (uint32_t)kCandCap : (uint32_t)kCandCap;
+    p.cand_words = p.row_off ? 2u * (uint32_t)kCandCap : (uint32_t)kCandCap;
+    // long queues: lazy form (pending block, one shift per ~30 accepted candidates); RG_LAZY_QUEUE_MIN_L moves the threshold
+    // (0 = never)
+    {
+        const uint32_t min_l = env_u32("RG_LAZY_QUEUE_MIN_L", 256);
+        p.lazy_queue = (min_l != 0 && p.L >= min_l && !p.vtab && !p.vt_smem) ? 1u : 0u;
+    }
+    const uint32_t cw = p.cand_words + (p.lazy_queue ? 2u * kPendSlots : 0u);
     uint32_t warps = 4, ctas = 0;
     uint32_t R = env_u32("RG_ROWS_PER_BATCH", 0);
     if (R == 0) {
