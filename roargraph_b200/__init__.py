@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
         L.rg_init.argtypes = [C.c_int]
         L.rg_device_sm_count.restype = C.c_int
         L.rg_index_create.argtypes = [C.POINTER(vp), vp, u64, u32, C.c_int, C.c_int]
+        L.rg_index_create_from_fbin.argtypes = [C.POINTER(vp), C.c_char_p, C.c_int, vp, vp, C.POINTER(u64), C.POINTER(u32)]
         L.rg_index_set_graph.argtypes = [vp, u32, vp, vp]
         L.rg_index_set_bipartite.argtypes = [vp, u64, vp, vp]
         L.rg_index_destroy.argtypes = [vp]
@@ -144,6 +145,28 @@ class RoarIndex:
             self._keep = base
             self.nd, self.dim = base.shape
             _check(lib().rg_index_create(C.byref(self._h), C.c_void_p(base.data_ptr()), self.nd, self.dim, m, 1))
+
+    ROW_HOOK = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_uint64, C.c_uint32, C.c_void_p)
+
+    @classmethod
+    def from_fbin(cls, path: str, metric: str | int, row_hook=None) -> "RoarIndex":
+        """The base streamed from an fbin file into HBM (rg_index_create_from_fbin: pinned double buffer, rows padded to x8
+        by the copy engine).  row_hook(rows: float32 [n, dim] numpy view of a staged slab, modified in place) is applied
+        to every slab before it is copied — e.g. the reference's row normalisation for cosine."""
+        self = cls.__new__(cls)
+        self._h, self._keep, self._owned = C.c_void_p(0), None, True
+        m = METRIC[metric] if isinstance(metric, str) else int(metric)
+        self.metric = m
+        cb = None
+        if row_hook is not None:
+            def _cb(ptr, n, dim, _user):
+                row_hook(np.ctypeslib.as_array(ptr, shape=(int(n), int(dim))))
+            cb = cls.ROW_HOOK(_cb)
+        nd, dim = C.c_uint64(0), C.c_uint32(0)
+        _check(lib().rg_index_create_from_fbin(C.byref(self._h), path.encode(), m, C.cast(cb, C.c_void_p) if cb else None, None,
+                                               C.byref(nd), C.byref(dim)))
+        self.nd, self.dim = nd.value, dim.value
+        return self
 
     @classmethod
     def _borrowed(cls, handle, nd: int, dim: int, metric: int) -> "RoarIndex":

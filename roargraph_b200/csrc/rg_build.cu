@@ -517,7 +517,10 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         batch = (nd + n_rounds - 1) / n_rounds;
     }
     batch = std::min(batch, nd);
-    const uint32_t exp_cap = std::min<uint32_t>(kMaxCand, L + 64);
+    // the connectivity search hands ALL its expanded nodes to the prune (full_retset, :1316); hops exceed L_pjpq by a few, and
+    // the prune pool holds kMaxCand candidates: refuse a queue length the pool would silently truncate
+    if (L + 64 > kMaxCand) { set_error("rg_index_build_roargraph: L_pjpq above 960 is not supported (prune pool of 1024 candidates)"); return RG_EINVAL; }
+    const uint32_t exp_cap = L + 64;
 
     Buf b_proj, b_supply, b_owner, b_keys_a, b_keys_b, b_cub, b_off, b_sum, b_best, b_exp_ids, b_exp_d, b_exp_cnt, b_out, b_maxdeg;
     int rc;

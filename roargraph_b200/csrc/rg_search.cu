@@ -1064,7 +1064,9 @@ __global__ void tags_reset_kernel(uint32_t *slot_epoch, uint32_t n_slots, uint32
 int maintain_tags(const SearchParams &p, const SearchLaunch &l, cudaStream_t s) {
     const uint32_t slots = l.grid * l.warps_per_cta;
     const uint32_t per_slot = (p.nq + slots - 1) / slots;
-    const uint32_t margin = std::min<uint32_t>(200u, 4u * per_slot + 8u);
+    // a slot is cleared here when its epoch could wrap during this launch: the dynamic tickets give a slot about per_slot
+    // queries, rarely more than 1.5x that (a slot that still overruns clears its own array inside the kernel)
+    const uint32_t margin = std::min<uint32_t>(250u, per_slot + per_slot / 2u + 8u);
     const uint32_t thr = 255u - margin;
     dim3 grid((unsigned)((p.tag_stride + kClearChunk - 1) / kClearChunk), slots);
     tags_clear_kernel<<<grid, 256, 0, s>>>(p.tags, p.slot_epoch, p.tag_stride, thr);

@@ -313,3 +313,93 @@ def test_live_reference_parity_at_scale(nb, dim, metric):
         assert_same_search(idx.search(c["queries"], 10, L), want, f"{metric} nb={nb} L={L}")
     c["R"].index_free(c["h"])
     idx.close()
+
+
+def test_index_from_fbin_streams_pads_and_hooks(tmp_path, oracle, golden):
+    """rg_index_create_from_fbin: the file streamed through the pinned staging buffers gives the index the padded (and, with
+    the row hook, normalised) rows a host-side load would have given it — same ids, distance bits, cmps, hops."""
+    from roargraph_b200 import formats as F
+    base, queries = golden.normalised(oracle)
+    bf = str(tmp_path / "base.fbin")
+    F.write_fbin(bf, golden.base_raw)
+    hook = None
+    if golden.metric == "cosine":
+        raw_dim = golden.base_raw.shape[1]
+        want_rows = base[:, :raw_dim]
+
+        def hook(rows):  # stand-in for the mirror's normalize_rows: hand the library the rows the reference's loader produces
+            lo = hook.done
+            rows[:] = want_rows[lo:lo + rows.shape[0]]
+            hook.done += rows.shape[0]
+        hook.done = 0
+    idx = rg.RoarIndex.from_fbin(bf, golden.metric, row_hook=hook)
+    assert (idx.nd, idx.dim) == base.shape
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    for L in golden.Ls:
+        want = {k: golden.z[f"{k}_L{L}"] for k in ("ids", "dists", "cmps", "hops")}
+        assert_same_search(idx.search(queries, golden.k, L), want, f"from_fbin {golden.name} L={L}")
+    idx.close()
+    # a dimension that is not a multiple of 8: padded with zeros by the copy, distances unchanged
+    rng = np.random.default_rng(4)
+    b13 = rng.standard_normal((3000, 13)).astype(np.float32)
+    q13 = F.pad_rows(rng.standard_normal((20, 13)).astype(np.float32))
+    F.write_fbin(bf, b13)
+    row_off, nbrs = random_graph(rng, 3000, 4, 12)
+    a = rg.RoarIndex.from_fbin(bf, "l2")
+    b = rg.RoarIndex(F.pad_rows(b13), "l2")
+    assert a.dim == 16
+    for x in (a, b):
+        x.set_graph(1, row_off, nbrs)
+    ra, rb = a.search(q13, 5, 30), b.search(q13, 5, 30)
+    assert all((u == v).all() for u, v in zip(ra[:1] + ra[2:], rb[:1] + rb[2:])) and (bits(ra[1]) == bits(rb[1])).all()
+    a.close()
+    b.close()
+    with pytest.raises(rg.RgError):
+        rg.RoarIndex.from_fbin(str(tmp_path / "missing.fbin"), "l2")
+    open(bf, "ab").write(b"xx")  # trailing bytes: "Data file size wrong!" like util.h:124
+    with pytest.raises(rg.RgError) as e:
+        rg.RoarIndex.from_fbin(bf, "l2")
+    assert "Data file size wrong" in str(e.value)
+
+
+def test_bipartite_graph_must_be_bipartite(oracle, golden):
+    """base -> base or query -> query edges would make the kernel read past the base array / the visited tags: rejected."""
+    base, _ = golden.normalised(oracle)
+    nd = base.shape[0]
+    idx = rg.RoarIndex(base, golden.metric)
+    row_off = np.zeros(nd + 3, dtype=np.uint64)
+    for bad in ([5], [nd + 1]):            # base node 0 -> base node 5; query node nd -> query node nd + 1
+        ro = row_off.copy()
+        if bad[0] < nd:
+            ro[1:] = 1
+        else:
+            ro[nd + 1:] = 1
+        with pytest.raises(rg.RgError) as e:
+            idx.set_bipartite(ro, np.array(bad, dtype=np.uint32))
+        assert e.value.code == rg.RG_EINVAL
+    idx.close()
+
+
+@pytest.mark.parametrize("min_l", ["0", "10"])
+def test_lazy_queue_equals_eager_queue(oracle, golden, monkeypatch, min_l):
+    """RG_LAZY_QUEUE_MIN_L: the pending-block queue (default for L_pq >= 256, forced from L_pq = 10 here) and the eager
+    sorted-array queue (0 = never lazy) are observably identical — and both equal the oracle — for short queues that overflow
+    inside a flush, long ones that never fill, k == L, and the bipartite search."""
+    base, queries = golden.normalised(oracle)
+    monkeypatch.setenv("RG_LAZY_QUEUE_MIN_L", min_l)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    for L in (10, 13, 31, 40, 64, 257, 700, 2000):
+        want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries, golden.k, L)
+        assert_same_search(idx.search(queries, golden.k, L), want, f"min_l={min_l} L={L}")
+    want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, queries[:9], 40, 40)
+    if not want["nfail"]:
+        assert_same_search(idx.search(queries[:9], 40, 40), want, "k == L")
+    row_off, nbrs = bipartite_from_knn(golden.z["train_knn_ids"], base.shape[0], 12)
+    init = np.random.default_rng(3).integers(0, base.shape[0], (queries.shape[0], 10)).astype(np.uint32)
+    idx.set_bipartite(row_off, nbrs)
+    for L in (10, 50, 300):
+        want = oracle.search_bipartite(base, row_off, nbrs, init, golden.metric, queries, 5, L)
+        if not want["nfail"]:
+            assert_same_search(idx.search_bipartite(queries, 5, L, init_ids=init), want, f"bipartite min_l={min_l} L={L}")
+    idx.close()
