@@ -755,7 +755,12 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
         // The filter leaves `reserve` bytes of shared memory per SM free so that merge CTAs fit beside its one CTA per SM.
         const uint64_t pair_q = 256;
         const uint64_t half = ((nqb / 2 + pair_q - 1) / pair_q) * pair_q;
-        static const bool two_lane_env = !(getenv("RG_KNN_LANES") && getenv("RG_KNN_LANES")[0] == '1');
+        // Opt-in (RG_KNN_LANES=2): measured SLOWER than one lane (151 552 queries, K = 100: 99.6 vs 82.1 ms against a 1.25 M-row
+        // shard, 516 vs 494 ms against 10 M rows, profiles/r2_knn_lanes_ab.txt).  With one merge CTA per query the small CTAs
+        // flood every SM's shared memory and keep the 195 KB filter CTAs of the other lane out until the merge is over (no
+        // overlap); with the persistent two-CTA-per-SM merge grid that does fit beside a filter CTA the gather is
+        // latency-bound (5.7 ms per half chunk at 0.7 TB/s against 3.8 ms HBM-bound for the whole chunk) and no longer hides.
+        static const bool two_lane_env = getenv("RG_KNN_LANES") && getenv("RG_KNN_LANES")[0] == '2';
         const int n_lanes = (tc && !pt.on && two_lane_env && nqb >= 2ull * (uint64_t)sms * 256u && half < nqb) ? 2 : 1;
         const uint32_t reserve = n_lanes == 2 ? 2u * (uint32_t)(fast_smem + 1536) : 0u;
         cudaStream_t ls[2] = {s, s};
