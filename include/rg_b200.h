@@ -149,6 +149,16 @@ int rg_knn_base_create(rg_knn_base **out, const float *base, uint64_t nb, uint32
 int rg_knn_base_destroy(rg_knn_base *kb);
 int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
                            int32_t *d_ids, float *d_dists, void *stream);
+/* Sharded base (G shards of one base, BASELINE configs[3]): the shards agree on ONE float per query before they filter.
+ * rg_knn_base_seed_dev writes, per query, an upper bound of the distance of the `rank`-th best row among the shard's first
+ * 65 536 rows (from the tensor-core scores alone; +inf when the shard is too small).  With rank = ceil(K / G) the MAXIMUM of
+ * the shards' values (one all-reduce of nq floats) bounds the GLOBAL K-th best distance: every shard holds >= rank rows at or
+ * below the maximum, G * rank >= K.  rg_knn_base_search_seeded_dev then scores the batch with that bound in force from row 0:
+ * a shard re-ranks ~K/4 instead of ~K * log2(rows) survivors per query.  Its per-shard lists may hold fewer than K entries
+ * (id -1, distance +inf behind them): every row of the global top-K is at or below the bound, so the MERGED top-K is exact. */
+int rg_knn_base_seed_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau, void *stream);
+int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
+                                  const float *d_tau, int32_t *d_ids, float *d_dists, void *stream);
 /* Device milliseconds per phase of this thread's kNN calls since the last rg_knn_profile_reset(), measured only when the
  * environment has RG_KNN_TRACE=1 (events + a synchronisation per phase: a diagnostic pass, never the timed one).
  * out[0..6] = base preparation, query conversion, tau seed pass, tensor-core filter, re-rank/merge, chunks, overflow retries. */

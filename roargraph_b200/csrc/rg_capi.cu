@@ -846,6 +846,17 @@ int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq,
     return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream);
 }
 
+int rg_knn_base_seed_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau, void *stream) {
+    if (!kb) { set_error("rg_knn_base_seed_dev: null base"); return RG_EINVAL; }
+    return knn_base_seed(kb, d_queries, nq, K, rank, d_tau, (cudaStream_t)stream);
+}
+
+int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
+                                  const float *d_tau, int32_t *d_ids, float *d_dists, void *stream) {
+    if (!kb) { set_error("rg_knn_base_search_seeded_dev: null base"); return RG_EINVAL; }
+    return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream, d_tau);
+}
+
 int rg_knn_profile(double *out7) {
     if (!out7) { set_error("rg_knn_profile: null buffer"); return RG_EINVAL; }
     const KnnProfile &p = knn_last_profile();

@@ -30,6 +30,7 @@ struct Nccl {
     ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string &err) {
         if (lib) return true;
@@ -44,8 +45,9 @@ struct Nccl {
         CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
         CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
         AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
         GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-        if (!CommInitAll || !CommDestroy || !AllGather || !GetErrorString) {
+        if (!CommInitAll || !CommDestroy || !AllGather || !AllReduce || !GetErrorString) {
             err = "libnccl.so.2 lacks a required symbol";
             return false;
         }
@@ -328,14 +330,14 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
         rg_knn_base *kb = nullptr;
         int rc = knn_base_new(&kb, d_base, d_base, hi - lo, dim, metric);  // the object owns d_base from here
         if (rc != RG_OK) return rc;
-        DevBuf<float> q, dd, out_d;
+        DevBuf<float> q, dd, out_d, tau;
         DevBuf<int32_t> di;
         DevBuf<uint32_t> out_i;
         DevBuf<unsigned long long> packed, gathered;
         if ((rc = q.reserve((size_t)G * per * dim)) == RG_OK && (rc = dd.reserve(batch * K)) == RG_OK &&
             (rc = di.reserve(batch * K)) == RG_OK && (rc = packed.reserve(batch * K)) == RG_OK &&
             (rc = gathered.reserve((size_t)G * batch * K)) == RG_OK && (rc = out_d.reserve(batch * K)) == RG_OK &&
-            (rc = out_i.reserve(batch * K)) == RG_OK) {
+            (rc = out_i.reserve(batch * K)) == RG_OK && (rc = tau.reserve(batch)) == RG_OK) {
             for (uint64_t q0 = 0; q0 < nq && rc == RG_OK; q0 += batch) {
                 const uint64_t n = std::min(batch, nq - q0);
                 const uint64_t pr = (n + G - 1) / G;  // rows of this batch uploaded by (and merged on) each GPU
@@ -349,7 +351,16 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
                     ncclResult_t r = g_nccl.AllGather(mine, q.p, pr * dim, ncclFloat, g->comm[s], st);
                     if (r != ncclSuccess) { rc = nccl_fail(r, "ncclAllGather(queries)"); break; }
                 }
-                rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st);
+                if (G > 1) {
+                    // the shards agree on one float per query before they filter (include/rg_b200.h, rg_knn_base_seed_dev)
+                    rc = knn_base_seed(kb, q.p, n, K, (K + G - 1) / G, tau.p, st);
+                    if (rc != RG_OK) break;
+                    ncclResult_t r = g_nccl.AllReduce(tau.p, tau.p, n, ncclFloat, ncclMax, g->comm[s], st);
+                    if (r != ncclSuccess) { rc = nccl_fail(r, "ncclAllReduce(tau)"); break; }
+                    rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st, tau.p);
+                } else {
+                    rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st);
+                }
                 if (rc != RG_OK) break;
                 rc = topk_pack_device(dd.p, reinterpret_cast<const uint32_t *>(di.p), n * K, (uint32_t)lo, packed.p, st);
                 if (rc != RG_OK) break;
@@ -371,6 +382,7 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
             }
         }
         q.release();
+        tau.release();
         dd.release();
         di.release();
         packed.release();

@@ -378,6 +378,15 @@ __global__ void knn_init_kernel(unsigned long long *top, uint64_t n_top, float *
     }
 }
 
+__global__ void knn_fill_kernel(float *x, uint64_t n, float v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+__global__ void knn_min_kernel(float *x, const float *y, uint64_t n) {  // x = min(x, y)
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = fminf(x[i], y[i]);
+}
+
 __global__ void knn_unpack_kernel(const unsigned long long *top, uint64_t n, int32_t id_offset, int32_t *ids, float *dists) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -645,8 +654,52 @@ int knn_base_prepare(rg_knn_base *kb, const float *d_base, uint64_t nb, uint32_t
 
 // One or more query batches against a prepared base.  tau_seed (optional, device, nq floats): an externally known upper
 // bound of every query's K-th best distance (e.g. agreed between the shards of a sharded base); the ramp then starts from it.
+// Seed bound for a SHARDED base: tau_out[q] = an upper bound of the distance of the `rank`-th best row of query q among this
+// shard's seed rows (the `rank`-th largest of the bf16 group maxima, widened by the bf16 bound; +inf when the shard is too
+// small for a seed pass).  With rank = ceil(K / G) on each of G shards, the MAXIMUM of the shards' values bounds the GLOBAL K-th
+// best distance: every shard holds >= rank rows at or below its own value, hence at or below the maximum — G * rank >= K rows.
+// One float per query crosses the ranks instead of per-shard candidate lists, and every shard then filters against a threshold
+// as tight as K-th-of-(G x 65 536 rows).
+int knn_base_seed(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau_out, cudaStream_t s) {
+    if (!kb || !d_queries || !d_tau_out) { set_error("rg_knn_base_seed: null buffer"); return RG_EINVAL; }
+    if (rank == 0 || rank > K) { set_error("rg_knn_base_seed: rank must be in [1, K]"); return RG_EINVAL; }
+    if (nq == 0) return RG_OK;
+    {
+        int dev = 0;
+        RG_CUDA(cudaGetDevice(&dev));
+        if (dev != kb->device) RG_CUDA(cudaSetDevice(kb->device));
+    }
+    Workspace *ws = current_ws();
+    if (!ws) { set_error("rg_knn: no current CUDA device"); return RG_ECUDA; }
+    const uint64_t n_seed = (kb->tc && kb->metric != RG_METRIC_COSINE) ? knn_tc_seed_rows(kb->nb, K) : 0;
+    if (!n_seed) {
+        knn_fill_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_tau_out, nq, INFINITY);
+        RG_CUDA(cudaGetLastError());
+        return RG_OK;
+    }
+    const uint32_t dim = kb->dim;
+    const uint64_t qb_max = (uint64_t)sm_count() * 256u * 4u;
+    const uint64_t qb_alloc = std::min<uint64_t>(nq, qb_max);
+    float *qn = nullptr, *seed_buf = nullptr;
+    void *q16 = nullptr;
+    RG_WS(ws, qn, WS_QN, nq * sizeof(float));
+    RG_WS(ws, q16, WS_Q16, qb_alloc * knn_tc_pitch(dim) * 2);
+    RG_WS(ws, seed_buf, WS_SEED, (n_seed / 128u) * qb_alloc * sizeof(float));
+    row_sqnorm_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, s>>>(d_queries, nq, dim, qn);
+    for (uint64_t qs = 0; qs < nq; qs += qb_max) {
+        const uint64_t nqb = std::min<uint64_t>(qb_max, nq - qs);
+        int rc = knn_tc_convert(d_queries + qs * dim, nqb, dim, q16, nullptr, s);
+        if (rc != RG_OK) return rc;
+        rc = knn_tc_seed(q16, nqb, kb->b16, kb->nb, dim, n_seed, rank, kb->metric_l2, qn + qs, kb->bn, kb->bmax, seed_buf, d_tau_out + qs,
+                         sm_count(), s);
+        if (rc != RG_OK) return rc;
+    }
+    RG_CUDA(cudaGetLastError());
+    return RG_OK;
+}
+
 int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
-                    float *d_dists, cudaStream_t s) {
+                    float *d_dists, cudaStream_t s, const float *d_tau_ext) {
     if (!kb || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
     const uint64_t nb = kb->nb;
     const uint32_t dim = kb->dim;
@@ -788,7 +841,10 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 RG_CUDA(cudaEventRecord(ev_init, s));
                 for (int l = 0; l < 2; ++l) RG_CUDA(cudaStreamWaitEvent(ls[l], ev_init, 0));
             }
-            const bool seeded = attempt == 0 && n_seed != 0;
+            // an externally agreed bound (sharded base: the maximum over the shards of their rank-ceil(K/G) seed values) replaces
+            // the local seed pass; it stays in force in the safe-mode retry as well (it is a bound, not a schedule)
+            if (d_tau_ext) knn_min_kernel<<<(unsigned)((nqb + 255) / 256), 256, 0, s>>>(tau, d_tau_ext + qs, nqb);
+            const bool seeded = attempt == 0 && n_seed != 0 && !d_tau_ext;
             if (seeded) {
                 pt.begin();
                 for (int l = 0; l < n_lanes; ++l) {
@@ -801,7 +857,8 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 pt.end(t_profile.seed_ms);
             }
             uint64_t lo = 0;
-            uint64_t csize = attempt == 1 ? (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap) : (seeded ? n_seed : chunk0);
+            uint64_t csize = attempt == 1 ? (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap)
+                                          : ((seeded || (d_tau_ext && tc)) ? std::max<uint64_t>(n_seed, 65536u) : chunk0);
             bool first_filter = true;
             while (lo < nb) {
                 const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
@@ -854,7 +911,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
                 // still fit in L2 (tensor-core path without a seed: the re-rank gather of those ~3K survivors never reaches
                 // DRAM, and the fixed per-launch cost of filter + merge dominates there)
-                if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && lo < 65536) ? 3 * lo : lo, chunk_max);
+                if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && !d_tau_ext && lo < 65536) ? 3 * lo : lo, chunk_max);
             }
             rc_lane = cudaGetLastError() == cudaSuccess ? RG_OK : RG_ECUDA;
             if (n_lanes == 2)
@@ -894,7 +951,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     t_profile = KnnProfile{};
     rg_knn_base *kb = new rg_knn_base();
     int rc = knn_base_prepare(kb, d_base, nb, dim, metric, /*from_ws=*/true, s);
-    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s);
+    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s, nullptr);
     knn_base_free(kb);
     return rc;
 }

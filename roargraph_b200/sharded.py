@@ -282,8 +282,9 @@ class ShardedKnn:
 
     `local_knn(base, q, K, metric, ids, dists, id_offset)` replaces the CUDA entry in the CPU tests."""
 
-    def __init__(self, d_base_shard, metric, row_lo: int, group=None, local_knn=None):
+    def __init__(self, d_base_shard, metric, row_lo: int, group=None, local_knn=None, share_tau: bool = True):
         self.group = group
+        self.share_tau = share_tau
         self.world, self.rank = _world(group)
         self.metric = metric
         self.row_lo = int(row_lo)
@@ -303,7 +304,17 @@ class ShardedKnn:
         if self._local is not None:
             return self._local(self._base, q, K, self.metric, ids, dists, self.row_lo)
         import torch
-        self._kb.search_dev(q, K, ids, dists, id_offset=0, stream=torch.cuda.current_stream())
+        import torch.distributed as dist
+        stream = torch.cuda.current_stream()
+        if self.world > 1 and self.share_tau:
+            # the shards agree on ONE float per query before they filter: each offers a bound of its ceil(K/G)-th best seed
+            # row, the maximum bounds the global K-th best distance (rg_knn_base_seed_dev); one all-reduce of nq floats
+            tau = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+            self._kb.seed_dev(q, K, -(-K // self.world), tau, stream=stream)
+            dist.all_reduce(tau, op=dist.ReduceOp.MAX, group=self.group)
+            self._kb.search_seeded_dev(q, K, tau, ids, dists, id_offset=0, stream=stream)
+        else:
+            self._kb.search_dev(q, K, ids, dists, id_offset=0, stream=stream)
 
     def search(self, d_queries, K: int, batch: int = 151552, slice_only: bool = False, out=None):
         """-> (ids int32 [nq, K], dists fp32 [nq, K]) on the device: internal distances ascending (-IP for "ip", squared

@@ -170,3 +170,46 @@ def test_knn_vs_mkl_reference_at_scale(knn_mode, metric, tmp_path):
     assert exact > 0.99, exact  # MKL-vs-MKL already differs on ~0.003 % of ids from ties
     recall = np.mean([len(set(a) & set(b)) for a, b in zip(ids[::97], ref_i[::97].astype(np.int32))]) / 100.0
     assert recall > 0.9999, recall
+
+
+def test_knn_shared_tau_across_shards_is_exact(knn_mode):
+    """The sharded-base protocol on one GPU: two shards of a 400 000-row base each offer a bound of their ceil(K/2)-th best seed
+    row (rg_knn_base_seed_dev), the maximum is put in force on both (rg_knn_base_search_seeded_dev), the per-shard lists —
+    now possibly shorter than K — are packed, merged, and must equal the unsharded answer bit for bit."""
+    if knn_mode != "tc":
+        pytest.skip("the seed pass belongs to the 2-CTA tensor-core filter")
+    import torch
+    rng = np.random.default_rng(8)
+    nb, nq, dim, K = 400_000, 3000, 200, 100
+    cent = rng.standard_normal((64, dim)).astype(np.float32)
+    base = (cent[rng.integers(0, 64, nb)] + 0.7 * rng.standard_normal((nb, dim))).astype(np.float32)
+    q = (cent[rng.integers(0, 64, nq)] + 0.9 * rng.standard_normal((nq, dim))).astype(np.float32)
+    d_base, d_q = torch.from_numpy(base).cuda(), torch.from_numpy(q).cuda()
+    for metric in ("ip", "l2"):
+        want_i, want_d = rg.knn(base, q, K, metric)
+        G, lo = 2, [0, nb // 2, nb]
+        shards = [rg.KnnBase(d_base[lo[g]:lo[g + 1]], metric) for g in range(G)]
+        taus = []
+        for kb in shards:
+            t = torch.empty(nq, dtype=torch.float32, device="cuda")
+            kb.seed_dev(d_q, K, -(-K // G), t)
+            taus.append(t)
+        tau = torch.maximum(taus[0], taus[1])
+        assert torch.isfinite(tau).all()
+        packed = torch.empty((G, nq, K), dtype=torch.int64, device="cuda")
+        short = 0
+        for g, kb in enumerate(shards):
+            li = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+            ld = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+            kb.search_seeded_dev(d_q, K, tau, li, ld)
+            short += int((li < 0).sum().item())
+            rg.topk_pack_dev(ld, li, lo[g], packed[g])
+        out_i = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+        out_d = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+        rg.topk_merge_packed_dev(packed, out_d, out_i)
+        torch.cuda.synchronize()
+        assert short > 0  # the shared bound really cut the per-shard lists below K
+        assert (out_i.cpu().numpy() == want_i).all(), metric
+        assert (out_d.cpu().numpy().view(np.uint32) == want_d.view(np.uint32)).all(), metric
+        for kb in shards:
+            kb.close()
