@@ -18,6 +18,7 @@
 // One CTA per node does candidate assembly, distances to the node, a bitonic sort by (distance, id) and the greedy
 // occlusion scan with the selected rows staged in shared memory.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <vector>
 
@@ -572,12 +573,26 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
     pp.in_off = b_off.as<uint64_t>();
 
     static const bool trace = getenv("RG_BUILD_TRACE") != nullptr;  // per-phase degree totals (synchronises), to stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto t_lap = t_last;
     auto report = [&](const char *what, const uint32_t *adj, uint32_t stride) {
         if (!trace) return;
         cudaStreamSynchronize(s);
+        const auto t_now = std::chrono::steady_clock::now();
+        const double sec = std::chrono::duration<double>(t_now - t_last).count();
         uint64_t nnz = 0;
         if (adjacency_nnz_device(adj, stride, nd, &nnz) == RG_OK)
-            fprintf(stderr, "[rg build] %-46s total degree %llu, avg %.4f\n", what, (unsigned long long)nnz, (double)nnz / nd);
+            fprintf(stderr, "[rg build] %-46s %7.2f s, total degree %llu, avg %.4f\n", what, sec, (unsigned long long)nnz,
+                    (double)nnz / nd);
+        t_last = std::chrono::steady_clock::now();
+    };
+    double t_search = 0, t_prune = 0, t_reverse = 0;  // connectivity phase split (trace only)
+    auto lap = [&](double &acc) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const auto t_now = std::chrono::steady_clock::now();
+        acc += std::chrono::duration<double>(t_now - t_lap).count();
+        t_lap = t_now;
     };
     // phase 1a: every training query's pruned list; the pivot keeps the list of its last query
     RG_CUDA(cudaMemsetAsync(b_owner.p, 0xff, (size_t)nd * 4, s));
@@ -655,13 +670,19 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         if (rc != RG_OK) return rc;
         sp.tags = idx->d_tags;
         sp.slot_epoch = idx->d_slot_epoch;
+        if (trace) {
+            cudaStreamSynchronize(s);
+            t_lap = std::chrono::steady_clock::now();
+        }
         rc = launch_build_search(sp, l, s);
         if (rc != RG_OK) return rc;
+        lap(t_search);
         pp.mode = 3;
         pp.node_lo = lo;
         pp.n_nodes = n;
         prune_kernel<<<n, kPruneThreads, smem, s>>>(pp);
         RG_CUDA(cudaGetLastError());
+        lap(t_prune);
         const unsigned long long *sorted = nullptr;
         rc = gather_offers(supply, sstride, lo, n, 2 * M, nd, b_keys_a.as<unsigned long long>(), b_keys_b.as<unsigned long long>(),
                            b_cub.p, cub_bytes, b_off.as<uint64_t>(), &sorted, s);
@@ -672,7 +693,11 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         pp.in_keys = sorted;
         prune_kernel<<<nd, kPruneThreads, smem, s>>>(pp);
         RG_CUDA(cudaGetLastError());
+        lap(t_reverse);
     }
+    if (trace)
+        fprintf(stderr, "[rg build] connectivity phase: beam search %.2f s, prune of the expanded sets %.2f s, reverse edges %.2f s\n",
+                t_search, t_prune, t_reverse);
     report("supply graph after connectivity enhancement (3)", supply, sstride);
     // phase 4
     pp.mode = 5;
