@@ -587,6 +587,7 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         t_last = std::chrono::steady_clock::now();
     };
     double t_search = 0, t_prune = 0, t_reverse = 0;  // connectivity phase split (trace only)
+    unsigned long long search_cmps = 0, search_adj = 0;
     auto lap = [&](double &acc) {
         if (!trace) return;
         cudaStreamSynchronize(s);
@@ -677,6 +678,12 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         rc = launch_build_search(sp, l, s);
         if (rc != RG_OK) return rc;
         lap(t_search);
+        if (trace) {  // evaluations of this round's searches -> gather bytes of the build's beam search
+            unsigned long long st[4] = {0, 0, 0, 0};
+            cudaMemcpy(st, idx->d_stats, sizeof(st), cudaMemcpyDeviceToHost);
+            search_cmps += st[0];
+            search_adj += st[2];
+        }
         pp.mode = 3;
         pp.node_lo = lo;
         pp.n_nodes = n;
@@ -696,8 +703,10 @@ int build_roargraph_device(rg_index *idx, const uint32_t *d_knn, uint64_t nsq, u
         lap(t_reverse);
     }
     if (trace)
-        fprintf(stderr, "[rg build] connectivity phase: beam search %.2f s, prune of the expanded sets %.2f s, reverse edges %.2f s\n",
-                t_search, t_prune, t_reverse);
+        fprintf(stderr, "[rg build] connectivity phase: beam search %.2f s (%.1f evaluations per node, %.0f GB/s of gathered rows + "
+                "adjacency), prune of the expanded sets %.2f s, reverse edges %.2f s\n",
+                t_search, (double)search_cmps / nd, ((double)(search_cmps + nd) * dim * 4.0 + (double)search_adj * 4.0) / t_search / 1e9,
+                t_prune, t_reverse);
     report("supply graph after connectivity enhancement (3)", supply, sstride);
     // phase 4
     pp.mode = 5;

@@ -911,7 +911,11 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
                 // still fit in L2 (tensor-core path without a seed: the re-rank gather of those ~3K survivors never reaches
                 // DRAM, and the fixed per-launch cost of filter + merge dominates there)
-                if (attempt == 0) csize = std::min<uint64_t>((tc && !seeded && !d_tau_ext && lo < 65536) ? 3 * lo : lo, chunk_max);
+                // with an externally agreed bound (sharded base) tau is tight from row 0 and tightens locally only once this
+                // shard's own list fills, so finer chunks buy nothing: the chunks grow 4x (three launch pairs over a 1.25 M-row
+                // shard instead of six; every pair costs a fixed ~1.4 ms per 151 552-query batch)
+                if (attempt == 0)
+                    csize = std::min<uint64_t>(d_tau_ext ? 3 * lo : (tc && !seeded && lo < 65536) ? 3 * lo : lo, chunk_max);
             }
             rc_lane = cudaGetLastError() == cudaSuccess ? RG_OK : RG_ECUDA;
             if (n_lanes == 2)
