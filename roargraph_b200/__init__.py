@@ -90,7 +90,7 @@ def lib() -> C.CDLL:
         L.rg_knn_base_destroy.argtypes = [vp]
         L.rg_knn_base_search_dev.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp]
         L.rg_knn_base_seed_dev.argtypes = [vp, vp, u64, u32, u32, vp, vp]
-        L.rg_knn_base_search_seeded_dev.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp, vp]
+        L.rg_knn_base_search_seeded_dev.argtypes = [vp, vp, u64, u32, i32, vp, u64, vp, vp, vp]
         L.rg_knn_profile.argtypes = [C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -357,11 +357,12 @@ class KnnBase:
         _check(lib().rg_knn_base_seed_dev(self._h, C.c_void_p(d_queries.data_ptr()), d_queries.shape[0], K, rank,
                                           C.c_void_p(d_tau.data_ptr()), _stream_ptr(stream)))
 
-    def search_seeded_dev(self, d_queries, K: int, d_tau, d_ids, d_dists, id_offset: int = 0, stream=None) -> None:
+    def search_seeded_dev(self, d_queries, K: int, d_tau, d_ids, d_dists, id_offset: int = 0, stream=None,
+                          bound_rows: int = 0) -> None:
         """search_dev with an externally agreed bound d_tau in force from row 0 (the per-shard lists may then hold fewer
         than K entries: id -1, distance +inf behind them)."""
         _check(lib().rg_knn_base_search_seeded_dev(self._h, C.c_void_p(d_queries.data_ptr()), d_queries.shape[0], K, id_offset,
-                                                   C.c_void_p(d_tau.data_ptr()), C.c_void_p(d_ids.data_ptr()),
+                                                   C.c_void_p(d_tau.data_ptr()), bound_rows, C.c_void_p(d_ids.data_ptr()),
                                                    C.c_void_p(d_dists.data_ptr()), _stream_ptr(stream)))
 
     def close(self) -> None:

@@ -852,9 +852,9 @@ int rg_knn_base_seed_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, u
 }
 
 int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
-                                  const float *d_tau, int32_t *d_ids, float *d_dists, void *stream) {
+                                  const float *d_tau, uint64_t bound_rows, int32_t *d_ids, float *d_dists, void *stream) {
     if (!kb) { set_error("rg_knn_base_search_seeded_dev: null base"); return RG_EINVAL; }
-    return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream, d_tau);
+    return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream, d_tau, bound_rows);
 }
 
 int rg_knn_profile(double *out7) {

@@ -357,7 +357,7 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
                     if (rc != RG_OK) break;
                     ncclResult_t r = g_nccl.AllReduce(tau.p, tau.p, n, ncclFloat, ncclMax, g->comm[s], st);
                     if (r != ncclSuccess) { rc = nccl_fail(r, "ncclAllReduce(tau)"); break; }
-                    rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st, tau.p);
+                    rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st, tau.p, (uint64_t)G * 65536u);
                 } else {
                     rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st);
                 }

@@ -171,7 +171,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
                int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s);
 int knn_base_prepare(rg_knn_base *kb, const float *d_base, uint64_t nb, uint32_t dim, int metric, bool from_ws, cudaStream_t s);
 int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
-                    float *d_dists, cudaStream_t s, const float *d_tau_ext = nullptr);
+                    float *d_dists, cudaStream_t s, const float *d_tau_ext = nullptr, uint64_t bound_rows = 0);
 int knn_base_seed(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau_out, cudaStream_t s);
 void knn_base_free(rg_knn_base *kb);
 // new object over device rows `d_base` (own_in: a device copy the object frees, or nullptr)

@@ -699,7 +699,7 @@ int knn_base_seed(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t
 }
 
 int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
-                    float *d_dists, cudaStream_t s, const float *d_tau_ext) {
+                    float *d_dists, cudaStream_t s, const float *d_tau_ext, uint64_t bound_rows) {
     if (!kb || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
     const uint64_t nb = kb->nb;
     const uint32_t dim = kb->dim;
@@ -830,10 +830,22 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
         const Lane lanes[2] = {{0, n_lanes == 2 ? half : nqb}, {half, nqb - half}};
         const uint32_t kp16 = tc ? knn_tc_pitch(dim) : 0;
         int rc_lane = RG_OK;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            // attempt 0: seeded tau (or tau = inf and a 256-row first chunk), chunks growing with the rows seen (expected
-            // survivors per chunk ~K); attempt 1 (after a candidate-list overflow): every chunk has at most `cap` rows,
-            // which cannot overflow.
+        // Schedules, tried in turn until no candidate list overflows:
+        //   kWhole   (only with an externally agreed bound, sharded base) the whole shard in ONE filter + merge launch pair: the
+        //            bound is tight from row 0 and tightens locally only once this shard's own list fills, so chunking buys
+        //            nothing and every launch pair costs a fixed ~1.4 ms per 151 552-query batch (expected survivors per query
+        //            ~ rows / (G * 65 536) * K, a few hundred against a list capacity of 2 048);
+        //   kGrowing seeded tau (or tau = inf and a 256-row first chunk), chunks growing with the rows seen (expected survivors
+        //            per chunk ~K);
+        //   kSafe    every chunk has at most `cap` rows, which cannot overflow.
+        enum { kWhole, kGrowing, kSafe };
+        static const bool whole_env = !(getenv("RG_KNN_WHOLE_SHARD") && getenv("RG_KNN_WHOLE_SHARD")[0] == '0');
+        // expected survivors per query with the bound in force over the whole shard: rows * K / (rows the bound is the K-th
+        // best of); x 2.5 for the bf16 band and the maximum over the shards, against one sub-list of cap / 2 entries
+        const bool whole_fits = bound_rows != 0 && (double)nb * K / (double)bound_rows * 2.5 <= (double)(cap / 2);
+        const int first_sched = (d_tau_ext && tc && whole_env && whole_fits) ? kWhole : kGrowing;
+        for (int sched = first_sched; sched <= kSafe; ++sched) {
+            const int attempt = sched == kSafe ? 1 : 0;
             const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
             knn_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, s>>>(top, nqb * K, tau, cnt, nqb);
             RG_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), s));
@@ -858,7 +870,8 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
             }
             uint64_t lo = 0;
             uint64_t csize = attempt == 1 ? (tc ? (uint64_t)(cap / 256u) * 256u : (uint64_t)cap)
-                                          : ((seeded || (d_tau_ext && tc)) ? std::max<uint64_t>(n_seed, 65536u) : chunk0);
+                             : sched == kWhole ? nb
+                                               : ((seeded || (d_tau_ext && tc)) ? std::max<uint64_t>(n_seed, 65536u) : chunk0);
             bool first_filter = true;
             while (lo < nb) {
                 const uint64_t hi = std::min<uint64_t>(nb, lo + csize);
@@ -929,7 +942,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
             if (rc_lane != RG_OK) { set_error("rg_knn: kernel launch failed"); break; }
             if (!h_ovf) break;
             t_profile.overflow_retries += 1;
-            if (attempt == 1) { set_error("rg_knn: candidate overflow in safe mode (internal error)"); rc_lane = RG_ENOMEM; break; }
+            if (sched == kSafe) { set_error("rg_knn: candidate overflow in safe mode (internal error)"); rc_lane = RG_ENOMEM; break; }
         }
         if (n_lanes == 2) {
             for (int l = 0; l < 2; ++l) {
@@ -955,7 +968,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     t_profile = KnnProfile{};
     rg_knn_base *kb = new rg_knn_base();
     int rc = knn_base_prepare(kb, d_base, nb, dim, metric, /*from_ws=*/true, s);
-    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s, nullptr);
+    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s, nullptr, 0);
     knn_base_free(kb);
     return rc;
 }

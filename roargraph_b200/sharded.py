@@ -312,7 +312,7 @@ class ShardedKnn:
             tau = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
             self._kb.seed_dev(q, K, -(-K // self.world), tau, stream=stream)
             dist.all_reduce(tau, op=dist.ReduceOp.MAX, group=self.group)
-            self._kb.search_seeded_dev(q, K, tau, ids, dists, id_offset=0, stream=stream)
+            self._kb.search_seeded_dev(q, K, tau, ids, dists, id_offset=0, stream=stream, bound_rows=self.world * 65536)
         else:
             self._kb.search_dev(q, K, ids, dists, id_offset=0, stream=stream)
 
