@@ -493,6 +493,7 @@ int rg_index_destroy(rg_index *idx) {
     idx->cmps.release();
     idx->hops.release();
     idx->init.release();
+    idx->order_scratch.release();
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
     return RG_OK;
@@ -665,6 +666,17 @@ static int search_dev(rg_index *idx, bool bipartite, const float *d_q, uint32_t 
         }
     }
     idx->last_launch = l;
+    // hand the batch out grouped by region (rg_search.cu, order_queries): worth it once the batch is several waves of the
+    // resident warps; RG_QUERY_ORDER=0 keeps the arrival order
+    {
+        static const bool order_env = !(getenv("RG_QUERY_ORDER") && getenv("RG_QUERY_ORDER")[0] == '0');
+        if (order_env && nq >= 4096 && idx->dim % 4 == 0) {
+            if ((rc = idx->order_scratch.reserve(2 * (size_t)nq + kLandmarks + 1)) != RG_OK) return rc;
+            rc = order_queries(idx->d_base, idx->nd, idx->dim, p.metric_l2, d_q, nq, idx->order_scratch.p, s);
+            if (rc != RG_OK) return rc;
+            p.order = idx->order_scratch.p + nq;
+        }
+    }
     return bipartite ? launch_bipartite(p, l, s) : launch_roargraph(p, l, s);
 }
 

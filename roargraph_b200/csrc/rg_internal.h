@@ -50,6 +50,7 @@ struct SearchParams {
     uint32_t row_stride_smem; // floats; == dim padded so that (stride % 32) == 16 (bank-conflict-free float4 reads)
     uint32_t warp_smem_bytes; // bytes of dynamic smem per warp
     int metric_l2;            // 1: squared L2, 0: negative inner product
+    const uint32_t *order;    // nq query indices in the order the tickets hand them out (nullptr: 0, 1, 2, ...)
     uint32_t cand_words;      // candidate-id scratch per warp (words)
     uint32_t lazy_queue;      // 1: long queue kept as sorted arrays + a pending block flushed every ~30 accepted candidates
     uint32_t drop_ep;         // 1: SearchRoarGraph — the entry point is not marked visited and may be evaluated again (9.1)
@@ -71,6 +72,10 @@ int plan_search(SearchParams &p, SearchLaunch &l, int sm_count, uint32_t max_slo
 int launch_roargraph(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
 int launch_bipartite(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
 int launch_build_search(const SearchParams &p, const SearchLaunch &l, cudaStream_t s);
+// order[0..nq) <- the batch's query indices grouped by their nearest of kLandmarks base rows (scratch: 2 * nq + kLandmarks + 1 words)
+constexpr uint32_t kLandmarks = 1024;
+int order_queries(const float *base, uint64_t nd, uint32_t dim, int metric_l2, const float *queries, uint32_t nq, uint32_t *scratch,
+                  cudaStream_t s);
 uint32_t max_search_slots(int sm_count);
 
 template <class T>
@@ -124,6 +129,7 @@ struct rg_index {
     unsigned long long *d_stats = nullptr;
     rg::DevBuf<float> q, dists;
     rg::DevBuf<uint32_t> ids, cmps, hops, init;
+    rg::DevBuf<uint32_t> order_scratch;  // query ordering: keys[nq] | order[nq] | bins[kLandmarks + 1]
     rg::SearchLaunch last_launch{};
     uint32_t last_k = 0;  // k of the last search (for the "not enough results" text)
     cudaStream_t stream = nullptr;  // used by the host-buffer entry points
