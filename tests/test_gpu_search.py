@@ -403,3 +403,30 @@ def test_lazy_queue_equals_eager_queue(oracle, golden, monkeypatch, min_l):
         if not want["nfail"]:
             assert_same_search(idx.search_bipartite(queries, 5, L, init_ids=init), want, f"bipartite min_l={min_l} L={L}")
     idx.close()
+
+
+def test_query_ordering_is_unobservable(oracle, golden, monkeypatch):
+    """RG_QUERY_ORDER=1 hands batches of >= 4 096 queries to the warps grouped by their nearest landmark row (an opt-in
+    experiment: no gain measured); every query is independent, so ids, distance bits, cmps and hops equal the arrival-order
+    run and the oracle, query by query."""
+    base, queries = golden.normalised(oracle)
+    reps = -(-5000 // queries.shape[0])
+    big = np.ascontiguousarray(np.tile(queries, (reps, 1))[:5000])
+    # make the rows distinct so that the ordering has something to sort (tiny perturbation, still the same graph)
+    big = (big + np.float32(1e-3) * np.random.default_rng(1).standard_normal(big.shape).astype(np.float32)).astype(np.float32)
+    if golden.metric == "cosine":
+        big /= np.linalg.norm(big, axis=1, keepdims=True)
+    idx = rg.RoarIndex(base, golden.metric)
+    idx.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    L = 40
+    want = oracle.search_roargraph(base, golden.row_off, golden.nbrs, golden.ep, golden.metric, big, golden.k, L)
+    monkeypatch.setenv("RG_QUERY_ORDER", "1")
+    got_ordered = idx.search(big, golden.k, L)
+    monkeypatch.setenv("RG_QUERY_ORDER", "0")
+    idx2 = rg.RoarIndex(base, golden.metric)
+    idx2.set_graph(golden.ep, golden.row_off, golden.nbrs)
+    got_plain = idx2.search(big, golden.k, L)
+    assert_same_search(got_ordered, want, "ordered tickets")
+    assert_same_search(got_plain, want, "arrival order")
+    idx.close()
+    idx2.close()
