@@ -839,7 +839,11 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
         //            per chunk ~K);
         //   kSafe    every chunk has at most `cap` rows, which cannot overflow.
         enum { kWhole, kGrowing, kSafe };
-        static const bool whole_env = !(getenv("RG_KNN_WHOLE_SHARD") && getenv("RG_KNN_WHOLE_SHARD")[0] == '0');
+        // RG_KNN_WHOLE_SHARD=1 opts in to kWhole; RG_KNN_EXT_GROWTH = growth factor of the chunks under an external bound
+        const char *we = getenv("RG_KNN_WHOLE_SHARD");
+        const bool whole_env = we && we[0] == '1';
+        const char *ge = getenv("RG_KNN_EXT_GROWTH");
+        const uint64_t ext_growth = ge ? std::max<uint64_t>(2, strtoull(ge, nullptr, 10)) : 2;
         // expected survivors per query with the bound in force over the whole shard: rows * K / (rows the bound is the K-th
         // best of); x 2.5 for the bf16 band and the maximum over the shards, against one sub-list of cap / 2 entries
         const bool whole_fits = bound_rows != 0 && (double)nb * K / (double)bound_rows * 2.5 <= (double)(cap / 2);
@@ -928,7 +932,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 // shard's own list fills, so finer chunks buy nothing: the chunks grow 4x (three launch pairs over a 1.25 M-row
                 // shard instead of six; every pair costs a fixed ~1.4 ms per 151 552-query batch)
                 if (attempt == 0)
-                    csize = std::min<uint64_t>(d_tau_ext ? 3 * lo : (tc && !seeded && lo < 65536) ? 3 * lo : lo, chunk_max);
+                    csize = std::min<uint64_t>(d_tau_ext ? (ext_growth - 1) * lo : (tc && !seeded && lo < 65536) ? 3 * lo : lo, chunk_max);
             }
             rc_lane = cudaGetLastError() == cudaSuccess ? RG_OK : RG_ECUDA;
             if (n_lanes == 2)
