@@ -16,6 +16,7 @@ import numpy as np
 
 import roargraph_b200 as rg
 
+_PACKED_MISSING = (0x7f800000 << 32) | 0xffffffff  # (+inf, no id): sorts after every real entry
 NO_ID = -1  # int32 view of the 0xffffffff "no result" sentinel the search kernel writes for a short result list
 
 
@@ -300,21 +301,15 @@ class ShardedKnn:
             self._kb.close()
             self._kb = None
 
-    def _local_knn(self, q, K, ids, dists):
-        if self._local is not None:
-            return self._local(self._base, q, K, self.metric, ids, dists, self.row_lo)
+    def _start_bound(self, q, K, tau):
+        """The shards agree on ONE float per query before they filter: each offers a bound of its ceil(K/G)-th best seed row,
+        the maximum bounds the global K-th best distance (rg_knn_base_seed_dev); one all-reduce of nq floats, started
+        asynchronously — search() issues it one batch AHEAD, so it travels under the previous batch's filter and is ordered
+        before that batch's result exchange on the communicator."""
         import torch
         import torch.distributed as dist
-        stream = torch.cuda.current_stream()
-        if self.world > 1 and self.share_tau:
-            # the shards agree on ONE float per query before they filter: each offers a bound of its ceil(K/G)-th best seed
-            # row, the maximum bounds the global K-th best distance (rg_knn_base_seed_dev); one all-reduce of nq floats
-            tau = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
-            self._kb.seed_dev(q, K, -(-K // self.world), tau, stream=stream)
-            dist.all_reduce(tau, op=dist.ReduceOp.MAX, group=self.group)
-            self._kb.search_seeded_dev(q, K, tau, ids, dists, id_offset=0, stream=stream, bound_rows=self.world * 65536)
-        else:
-            self._kb.search_dev(q, K, ids, dists, id_offset=0, stream=stream)
+        self._kb.seed_dev(q, K, -(-K // self.world), tau[:q.shape[0]], stream=torch.cuda.current_stream())
+        return dist.all_reduce(tau[:q.shape[0]], op=dist.ReduceOp.MAX, group=self.group, async_op=True)
 
     def search(self, d_queries, K: int, batch: int = 151552, slice_only: bool = False, out=None):
         """-> (ids int32 [nq, K], dists fp32 [nq, K]) on the device: internal distances ascending (-IP for "ip", squared
@@ -330,38 +325,60 @@ class ShardedKnn:
         cuda = d_queries.is_cuda
         if cuda and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=dev)
+        shared = cuda and self._local is None and G > 1 and self.share_tau
         bufs = [None, None]
         events = [None, None]
-        for bi, lo in enumerate(range(0, nq, batch)):
+        taus = [torch.empty(min(nq, batch), dtype=torch.float32, device=dev) for _ in range(2)] if shared else None
+        starts = list(range(0, nq, batch))
+        bound = self._start_bound(d_queries[0:min(nq, batch)], K, taus[0]) if shared and starts else None
+        for bi, lo in enumerate(starts):
             hi = min(nq, lo + batch)
             n = hi - lo
             slot = bi & 1
-            if bufs[slot] is None or bufs[slot][0].shape[0] < n:
+            per = -(-n // G)
+            if bufs[slot] is None:
                 bufs[slot] = (torch.empty((batch, K), dtype=torch.int32, device=dev),
                               torch.empty((batch, K), dtype=torch.float32, device=dev),
-                              torch.empty((batch, K), dtype=torch.int64, device=dev),
-                              torch.empty((G * batch, K), dtype=torch.int64, device=dev))
+                              torch.empty((G * (-(-batch // G)), K), dtype=torch.int64, device=dev),
+                              torch.empty((G * (-(-batch // G)) if slice_only else G * batch, K), dtype=torch.int64, device=dev))
             loc_i, loc_d, packed, gathered = bufs[slot]
             if cuda and events[slot] is not None:
                 torch.cuda.current_stream().wait_event(events[slot])  # the exchange that last used this slot has finished
-            self._local_knn(d_queries[lo:hi], K, loc_i[:n], loc_d[:n])
-            if self._local is not None:  # the CPU checker already returns global ids
-                pack_topk(loc_d[:n], loc_i[:n], 0, out=packed[:n])
+            q = d_queries[lo:hi]
+            if shared:
+                bound.wait()                                         # this batch's bound (started one batch ago)
+                tau = taus[slot]
+                if bi + 1 < len(starts):
+                    nlo = starts[bi + 1]
+                    bound = self._start_bound(d_queries[nlo:min(nq, nlo + batch)], K, taus[slot ^ 1])
+                self._kb.search_seeded_dev(q, K, tau[:n], loc_i[:n], loc_d[:n], id_offset=0, stream=torch.cuda.current_stream(),
+                                           bound_rows=G * 65536)
+            elif self._local is not None:
+                self._local(self._base, q, K, self.metric, loc_i[:n], loc_d[:n], self.row_lo)
             else:
-                pack_topk(loc_d[:n], loc_i[:n], self.row_lo, out=packed[:n])
-            if slice_only:
-                per = -(-n // G)
-                q_lo, q_hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
-            else:
-                q_lo, q_hi = 0, n
+                self._kb.search_dev(q, K, loc_i[:n], loc_d[:n], id_offset=0, stream=torch.cuda.current_stream())
+            if slice_only and G > 1 and G * per != n:
+                packed[n:G * per].fill_(_PACKED_MISSING)             # ragged tail: the last ranks' slices are padded
+            # the CPU checker already returns global ids
+            pack_topk(loc_d[:n], loc_i[:n], 0 if self._local is not None else self.row_lo, out=packed[:n])
 
             def exchange():
+                if slice_only and G > 1:
+                    # a rank merges only its own slice of the batch: it needs that slice of every shard's block, nothing
+                    # else — an all-to-all of [per, K] pieces, 1/G of the all-gather's traffic
+                    g = gathered[:G * per]
+                    dist.all_to_all_single(g, packed[:G * per], group=self.group)
+                    q_lo, q_hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
+                    if q_hi > q_lo:
+                        merge_packed(g.view(G, per, K), out_d[lo + q_lo:lo + q_lo + per], out_i[lo + q_lo:lo + q_lo + per], 0,
+                                     q_hi - q_lo, stream=torch.cuda.current_stream() if cuda else None)
+                    return
                 g = gathered[:G * n]
                 if G > 1:
                     dist.all_gather_into_tensor(g, packed[:n], group=self.group)
                 else:
                     g.copy_(packed[:n])
-                merge_packed(g.view(G, n, K), out_d[lo:hi], out_i[lo:hi], q_lo, q_hi,
+                merge_packed(g.view(G, n, K), out_d[lo:hi], out_i[lo:hi], 0, n,
                              stream=torch.cuda.current_stream() if cuda else None)
 
             if cuda:
