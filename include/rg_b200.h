@@ -161,6 +161,17 @@ int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq,
 int rg_knn_base_seed_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau, void *stream);
 int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
                                   const float *d_tau, uint64_t bound_rows, int32_t *d_ids, float *d_dists, void *stream);
+/* The same with ONE re-sync of the bound inside the shard: at the first chunk boundary at or past `resync_rows` rows (after the
+ * last chunk when the shard is shorter, so that every shard calls the hook the same number of times: once per batch of up to
+ * 151 552 queries) the shard writes its `rank`-th best EXACT distance so far into d_bound[q] (+inf while its list is shorter)
+ * and calls hook(user, q_off, n, stream), which must reduce d_bound[q_off, q_off + n) to the MAXIMUM over the shards on
+ * `stream` (one all-reduce) and return RG_OK; the search then continues with tau = min(tau, d_bound).  With rank * G >= K the
+ * maximum bounds the global K-th best distance exactly like the seed bound, but from re-ranked rows of a fifth of the base
+ * instead of the seed rows' scores, so the rest of the shard passes ~K/G instead of ~2.5 K/G survivors per query. */
+typedef int (*rg_knn_bound_hook)(void *user, uint64_t q_off, uint64_t n, void *stream);
+int rg_knn_base_search_resync_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
+                                  const float *d_tau, uint64_t bound_rows, uint32_t rank, uint64_t resync_rows, float *d_bound,
+                                  rg_knn_bound_hook hook, void *user, int32_t *d_ids, float *d_dists, void *stream);
 /* Device milliseconds per phase of this thread's kNN calls since the last rg_knn_profile_reset(), measured only when the
  * environment has RG_KNN_TRACE=1 (events + a synchronisation per phase: a diagnostic pass, never the timed one).
  * out[0..6] = base preparation, query conversion, tau seed pass, tensor-core filter, re-rank/merge, chunks, overflow retries. */

@@ -91,9 +91,14 @@ def lib() -> C.CDLL:
         L.rg_knn_base_search_dev.argtypes = [vp, vp, u64, u32, i32, vp, vp, vp]
         L.rg_knn_base_seed_dev.argtypes = [vp, vp, u64, u32, u32, vp, vp]
         L.rg_knn_base_search_seeded_dev.argtypes = [vp, vp, u64, u32, i32, vp, u64, vp, vp, vp]
+        L.rg_knn_base_search_resync_dev.argtypes = [vp, vp, u64, u32, i32, vp, u64, u32, u64, vp, KNN_BOUND_HOOK, vp, vp, vp, vp]
         L.rg_knn_profile.argtypes = [C.POINTER(C.c_double)]
         _lib = L
     return _lib
+
+
+# int hook(void *user, uint64_t q_off, uint64_t n, void *stream)  (include/rg_b200.h: rg_knn_bound_hook)
+KNN_BOUND_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)
 
 
 def _check(rc: int) -> None:
@@ -364,6 +369,30 @@ class KnnBase:
         _check(lib().rg_knn_base_search_seeded_dev(self._h, C.c_void_p(d_queries.data_ptr()), d_queries.shape[0], K, id_offset,
                                                    C.c_void_p(d_tau.data_ptr()), bound_rows, C.c_void_p(d_ids.data_ptr()),
                                                    C.c_void_p(d_dists.data_ptr()), _stream_ptr(stream)))
+
+    def search_resync_dev(self, d_queries, K: int, d_tau, d_ids, d_dists, rank: int, resync_rows: int, d_bound, reduce_max,
+                          id_offset: int = 0, stream=None, bound_rows: int = 0) -> None:
+        """search_seeded_dev with ONE re-sync of the bound inside the shard (rg_knn_base_search_resync_dev): at the first
+        chunk boundary at or past `resync_rows` the shard's rank-th best exact distances so far are in d_bound[q_off:q_off+n]
+        and reduce_max(q_off, n) must reduce that slice to the maximum over the shards on the current stream."""
+        failure = []
+
+        def hook(_user, q_off, n, _stream):
+            try:
+                reduce_max(int(q_off), int(n))
+                return 0
+            except Exception as e:  # an exception must not unwind through the C frames
+                failure.append(e)
+                return RG_ECUDA
+
+        cb = KNN_BOUND_HOOK(hook)
+        rc = lib().rg_knn_base_search_resync_dev(self._h, C.c_void_p(d_queries.data_ptr()), d_queries.shape[0], K, id_offset,
+                                                 C.c_void_p(d_tau.data_ptr()), bound_rows, rank, resync_rows,
+                                                 C.c_void_p(d_bound.data_ptr()), cb, None, C.c_void_p(d_ids.data_ptr()),
+                                                 C.c_void_p(d_dists.data_ptr()), _stream_ptr(stream))
+        if failure:
+            raise failure[0]
+        _check(rc)
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:

@@ -872,6 +872,15 @@ int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint6
     return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream, d_tau, bound_rows);
 }
 
+int rg_knn_base_search_resync_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
+                                  const float *d_tau, uint64_t bound_rows, uint32_t rank, uint64_t resync_rows, float *d_bound,
+                                  rg_knn_bound_hook hook, void *user, int32_t *d_ids, float *d_dists, void *stream) {
+    if (!kb) { set_error("rg_knn_base_search_resync_dev: null base"); return RG_EINVAL; }
+    if (!d_tau) { set_error("rg_knn_base_search_resync_dev: needs the seed bound (rg_knn_base_seed_dev)"); return RG_EINVAL; }
+    KnnResync rs{rank, resync_rows, d_bound, hook, user};
+    return knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, (cudaStream_t)stream, d_tau, bound_rows, &rs);
+}
+
 int rg_knn_profile(double *out7) {
     if (!out7) { set_error("rg_knn_profile: null buffer"); return RG_EINVAL; }
     const KnnProfile &p = knn_last_profile();

@@ -316,6 +316,13 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
     if (const char *hb = getenv("RG_KNN_HOST_BATCH")) batch = std::max<uint64_t>(1, strtoull(hb, nullptr, 10));
     batch = std::min(batch, nq);
     const uint64_t per = (batch + G - 1) / G;
+    // the same re-sync point on every shard: a fifth of the smallest shard, on the chunk grid (rg_knn.cu)
+    // (RG_KNN_RESYNC=1 enables it: worth ~2 % on one rank's share of the 8-way 10 M x 10 M job, less than the all-reduce it
+    // adds costs when the ranks are out of step, profiles/r2_knn_shard_schedules.txt)
+    uint64_t resync_rows = (nb / G) / 5;
+    if (const char *rr = getenv("RG_KNN_RESYNC_ROWS")) resync_rows = strtoull(rr, nullptr, 10);
+    const char *re = getenv("RG_KNN_RESYNC");
+    const bool resync_on = re && re[0] == '1';
     return run_on_all(g, [&](int s) {
         cudaStream_t st = g->stream[s];
         const uint64_t lo = shard_lo(nb, s, G), hi = shard_lo(nb, s + 1, G);
@@ -330,14 +337,14 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
         rg_knn_base *kb = nullptr;
         int rc = knn_base_new(&kb, d_base, d_base, hi - lo, dim, metric);  // the object owns d_base from here
         if (rc != RG_OK) return rc;
-        DevBuf<float> q, dd, out_d, tau;
+        DevBuf<float> q, dd, out_d, tau, bound;
         DevBuf<int32_t> di;
         DevBuf<uint32_t> out_i;
         DevBuf<unsigned long long> packed, gathered;
         if ((rc = q.reserve((size_t)G * per * dim)) == RG_OK && (rc = dd.reserve(batch * K)) == RG_OK &&
             (rc = di.reserve(batch * K)) == RG_OK && (rc = packed.reserve(batch * K)) == RG_OK &&
             (rc = gathered.reserve((size_t)G * batch * K)) == RG_OK && (rc = out_d.reserve(batch * K)) == RG_OK &&
-            (rc = out_i.reserve(batch * K)) == RG_OK && (rc = tau.reserve(batch)) == RG_OK) {
+            (rc = out_i.reserve(batch * K)) == RG_OK && (rc = tau.reserve(batch)) == RG_OK && (rc = bound.reserve(batch)) == RG_OK) {
             for (uint64_t q0 = 0; q0 < nq && rc == RG_OK; q0 += batch) {
                 const uint64_t n = std::min(batch, nq - q0);
                 const uint64_t pr = (n + G - 1) / G;  // rows of this batch uploaded by (and merged on) each GPU
@@ -357,7 +364,18 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
                     if (rc != RG_OK) break;
                     ncclResult_t r = g_nccl.AllReduce(tau.p, tau.p, n, ncclFloat, ncclMax, g->comm[s], st);
                     if (r != ncclSuccess) { rc = nccl_fail(r, "ncclAllReduce(tau)"); break; }
-                    rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st, tau.p, (uint64_t)G * 65536u);
+                    // ... and once more inside the shard, from the rows re-ranked so far (rg_knn_base_search_resync_dev)
+                    struct HookCtx { rg_group *g; int s; float *bound; ncclResult_t r; } hc{g, s, bound.p, ncclSuccess};
+                    KnnResync rs{(K + G - 1) / G, resync_rows, bound.p,
+                                 [](void *u, uint64_t q_off, uint64_t cnt, void *stream) -> int {
+                                     HookCtx *c = static_cast<HookCtx *>(u);
+                                     c->r = g_nccl.AllReduce(c->bound + q_off, c->bound + q_off, cnt, ncclFloat, ncclMax, c->g->comm[c->s],
+                                                             (cudaStream_t)stream);
+                                     return c->r == ncclSuccess ? RG_OK : RG_ECUDA;
+                                 },
+                                 &hc};
+                    rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st, tau.p, (uint64_t)G * 65536u, resync_on ? &rs : nullptr);
+                    if (hc.r != ncclSuccess) { rc = nccl_fail(hc.r, "ncclAllReduce(bound)"); break; }
                 } else {
                     rc = knn_base_search(kb, q.p, n, K, 0, di.p, dd.p, st);
                 }
@@ -383,6 +401,7 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
         }
         q.release();
         tau.release();
+        bound.release();
         dd.release();
         di.release();
         packed.release();

@@ -176,8 +176,17 @@ int adjacency_nnz_device(const uint32_t *d_adj, uint32_t stride, uint64_t nd, ui
 int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_t nq, uint32_t dim, uint32_t K,
                int metric, int32_t id_offset, int32_t *d_ids, float *d_dists, cudaStream_t s);
 int knn_base_prepare(rg_knn_base *kb, const float *d_base, uint64_t nb, uint32_t dim, int metric, bool from_ws, cudaStream_t s);
+// mid-shard re-sync of the shared bound (include/rg_b200.h, rg_knn_base_search_resync_dev)
+struct KnnResync {
+    uint32_t rank;      // every shard publishes its rank-th best exact distance so far, rank * G >= K
+    uint64_t rows;      // at the first chunk boundary at or past this many rows
+    float *d_bound;     // nq floats, caller-owned, device
+    int (*hook)(void *user, uint64_t q_off, uint64_t n, void *stream);  // reduce d_bound[q_off, q_off + n) to the MAX over the shards
+    void *user;
+};
 int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
-                    float *d_dists, cudaStream_t s, const float *d_tau_ext = nullptr, uint64_t bound_rows = 0);
+                    float *d_dists, cudaStream_t s, const float *d_tau_ext = nullptr, uint64_t bound_rows = 0,
+                    const KnnResync *resync = nullptr);
 int knn_base_seed(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau_out, cudaStream_t s);
 void knn_base_free(rg_knn_base *kb);
 // new object over device rows `d_base` (own_in: a device copy the object frees, or nullptr)

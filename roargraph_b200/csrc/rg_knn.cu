@@ -169,6 +169,37 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long *sk, uint32
     }
 }
 
+// the same network for m <= 64, run by ONE warp (lane i owns comparator i): no block barrier per step
+__device__ __forceinline__ void bitonic_sort_warp(unsigned long long *sk, uint32_t m) {
+    const uint32_t i = threadIdx.x & 31;
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            if (i < (m >> 1)) {
+                const uint32_t lo = 2 * i - (i & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == up) {
+                    sk[lo] = b;
+                    sk[hi] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// number of entries of the ascending list a[0, n) below `key`
+__device__ __forceinline__ uint32_t count_below(const unsigned long long *a, uint32_t n, unsigned long long key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
 // General path (any candidate count up to cap): one CTA of 256 threads per query of the work list.
 __device__ void merge_query_big(uint64_t q, unsigned long long *__restrict__ top, uint32_t K, unsigned long long *__restrict__ cand,
                                 uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau, uint32_t sort_n,
@@ -267,7 +298,7 @@ __global__ void knn_merge_kernel(unsigned long long *__restrict__ top, uint32_t 
 // candidates (more: the query goes to the work list of the general kernel).  Exact fp32 distances of eight candidates per
 // warp pass (128-bit row loads when VEC), candidates that do not beat the current K-th best are dropped before the sort,
 // and the sort buffer holds only `sn` words, so sixteen queries are resident per SM and the gather latencies overlap.
-template <bool VEC>
+template <bool VEC, bool kMergeByRank = true>
 __global__ void __launch_bounds__(128) knn_merge_fast_kernel(unsigned long long *__restrict__ top, uint32_t K,
                                                              const unsigned long long *__restrict__ cand,
                                                              uint32_t *__restrict__ cand_cnt, uint32_t cap, float *__restrict__ tau,
@@ -349,19 +380,45 @@ __global__ void __launch_bounds__(128) knn_merge_fast_kernel(unsigned long long 
     }
     __syncthreads();
     const uint32_t kept = s_kept;
-    if (kept) {
+    uint32_t m2 = 1;
+    while (m2 < kept) m2 <<= 1;
+    if (kept && kMergeByRank && m2 + K <= sn) {
+        // The current list is already sorted: sort the `kept` new entries alone (typically ~K/2: a 64-entry network inside one
+        // warp instead of a 256-entry one with a block barrier per step) and merge by RANK — entry i of one list lands at
+        // i + (entries of the other list below it); the keys (distance, id) are unique, so this is the full sort's order.
+        unsigned long long *st = sk + m2;
+        for (uint32_t i = kept + threadIdx.x; i < m2; i += blockDim.x) sk[i] = ~0ull;
+        for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) st[i] = top[q * K + i];
+        __syncthreads();
+        if (m2 <= 64) {
+            if (warp == 0) bitonic_sort_warp(sk, m2);
+            __syncthreads();
+        } else {
+            bitonic_sort_smem(sk, m2);
+        }
+        for (uint32_t i = threadIdx.x; i < kept + K; i += blockDim.x) {
+            const bool fresh = i < kept;
+            const unsigned long long key = fresh ? sk[i] : st[i - kept];
+            const uint32_t pos = fresh ? i + count_below(st, K, key) : (i - kept) + count_below(sk, kept, key);
+            if (pos < K) {
+                top[q * K + pos] = key;
+                // tau only tightens (it may have been seeded)
+                if (pos == K - 1 && key != ~0ull) tau[q] = fminf(tau[q], ord2f((uint32_t)(key >> 32)));
+            }
+        }
+    } else if (kept) {
         uint32_t m = 1;
         while (m < kept + K) m <<= 1;  // <= sn because kept <= n
         for (uint32_t i = kept + threadIdx.x; i < m; i += blockDim.x) sk[i] = i < kept + K ? top[q * K + (i - kept)] : ~0ull;
         __syncthreads();
         bitonic_sort_smem(sk, m);
         for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) top[q * K + i] = sk[i];
+        if (threadIdx.x == 0) {
+            const unsigned long long nk = sk[K - 1];
+            if (nk != ~0ull) tau[q] = fminf(tau[q], ord2f((uint32_t)(nk >> 32)));
+        }
     }
     if (threadIdx.x == 0) {
-        if (kept) {
-            const unsigned long long nk = sk[K - 1];
-            if (nk != ~0ull) tau[q] = fminf(tau[q], ord2f((uint32_t)(nk >> 32)));  // tau only tightens (it may have been seeded)
-        }
         cand_cnt[2 * q] = 0;
         cand_cnt[2 * q + 1] = 0;
     }
@@ -385,6 +442,14 @@ __global__ void knn_fill_kernel(float *x, uint64_t n, float v) {
 __global__ void knn_min_kernel(float *x, const float *y, uint64_t n) {  // x = min(x, y)
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = fminf(x[i], y[i]);
+}
+
+// bound[q] = exact distance of the rank-th best row found so far for query q (+inf while the list is shorter)
+__global__ void knn_rank_kernel(const unsigned long long *top, uint32_t K, uint32_t rank, uint64_t nq, float *bound) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const unsigned long long v = top[q * K + rank - 1];
+    bound[q] = (v == ~0ull) ? INFINITY : ord2f((uint32_t)(v >> 32));
 }
 
 __global__ void knn_unpack_kernel(const unsigned long long *top, uint64_t n, int32_t id_offset, int32_t *ids, float *dists) {
@@ -699,12 +764,16 @@ int knn_base_seed(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t
 }
 
 int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset, int32_t *d_ids,
-                    float *d_dists, cudaStream_t s, const float *d_tau_ext, uint64_t bound_rows) {
+                    float *d_dists, cudaStream_t s, const float *d_tau_ext, uint64_t bound_rows, const KnnResync *resync) {
     if (!kb || !d_queries || !d_ids || !d_dists) { set_error("rg_knn: null buffer"); return RG_EINVAL; }
     const uint64_t nb = kb->nb;
     const uint32_t dim = kb->dim;
     if (K == 0 || K > nb) { set_error("rg_knn: K must be in [1, nb]"); return RG_EINVAL; }
     if (K > 1024) { set_error("rg_knn: K > 1024 not supported"); return RG_EINVAL; }
+    if (resync && (!resync->hook || !resync->d_bound || resync->rank == 0 || resync->rank > K)) {
+        set_error("rg_knn: re-sync needs a hook, a bound buffer and a rank in [1, K]");
+        return RG_EINVAL;
+    }
     if (nq == 0) return RG_OK;
     {
         int dev = 0;
@@ -788,8 +857,12 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
     const size_t fast_smem = (size_t)fast_sn * 8 + (size_t)dim * 4;
     const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(kb->B) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
     rr.vec = vec ? 1 : 0;
-    RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-    RG_CUDA(cudaFuncSetAttribute(knn_merge_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    // RG_KNN_MERGE_RANK=0: the earlier full sort of new + current entries (A/B and a second implementation for the tests)
+    const char *mr = getenv("RG_KNN_MERGE_RANK");
+    const bool by_rank = !(mr && mr[0] == '0');
+    auto fast_kernel = vec ? (by_rank ? knn_merge_fast_kernel<true, true> : knn_merge_fast_kernel<true, false>)
+                           : (by_rank ? knn_merge_fast_kernel<false, true> : knn_merge_fast_kernel<false, false>);
+    RG_CUDA(cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
     uint32_t *work_cnt = worklist + qb_alloc;
 
     for (uint64_t qs = 0; qs < nq; qs += qb_max) {
@@ -814,7 +887,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
         // overlap); with the persistent two-CTA-per-SM merge grid that does fit beside a filter CTA the gather is
         // latency-bound (5.7 ms per half chunk at 0.7 TB/s against 3.8 ms HBM-bound for the whole chunk) and no longer hides.
         static const bool two_lane_env = getenv("RG_KNN_LANES") && getenv("RG_KNN_LANES")[0] == '2';
-        const int n_lanes = (tc && !pt.on && two_lane_env && nqb >= 2ull * (uint64_t)sms * 256u && half < nqb) ? 2 : 1;
+        const int n_lanes = (tc && !pt.on && two_lane_env && !resync && nqb >= 2ull * (uint64_t)sms * 256u && half < nqb) ? 2 : 1;
         const uint32_t reserve = n_lanes == 2 ? 2u * (uint32_t)(fast_smem + 1536) : 0u;
         cudaStream_t ls[2] = {s, s};
         cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_init = nullptr;
@@ -848,6 +921,11 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
         // best of); x 2.5 for the bf16 band and the maximum over the shards, against one sub-list of cap / 2 entries
         const bool whole_fits = bound_rows != 0 && (double)nb * K / (double)bound_rows * 2.5 <= (double)(cap / 2);
         const int first_sched = (d_tau_ext && tc && whole_env && whole_fits) ? kWhole : kGrowing;
+        // Re-sync of the shared bound (sharded base): ONCE per query batch, at the first chunk boundary at or past
+        // resync->rows (or after the last chunk, so that every shard makes the same number of hook calls whatever its size and
+        // schedule), the shard publishes its rank-th best exact distance so far, the hook reduces it to the maximum over the
+        // shards, and tau = min(tau, that).  The reduced bound stays valid for a retry in safe mode, which re-applies it.
+        bool resynced = false;
         for (int sched = first_sched; sched <= kSafe; ++sched) {
             const int attempt = sched == kSafe ? 1 : 0;
             const uint64_t n_init = std::max<uint64_t>(nqb * K, nqb);
@@ -860,6 +938,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
             // an externally agreed bound (sharded base: the maximum over the shards of their rank-ceil(K/G) seed values) replaces
             // the local seed pass; it stays in force in the safe-mode retry as well (it is a bound, not a schedule)
             if (d_tau_ext) knn_min_kernel<<<(unsigned)((nqb + 255) / 256), 256, 0, s>>>(tau, d_tau_ext + qs, nqb);
+            if (resynced) knn_min_kernel<<<(unsigned)((nqb + 255) / 256), 256, 0, s>>>(tau, resync->d_bound + qs, nqb);
             const bool seeded = attempt == 0 && n_seed != 0 && !d_tau_ext;
             if (seeded) {
                 pt.begin();
@@ -912,8 +991,7 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                         // two lanes: a persistent grid of two CTAs per SM, which fits beside the other lane's filter CTA (one CTA per
                         // query would flood every SM's shared memory and keep the 195 KB filter CTAs out until the merge is over)
                         const unsigned mgrid = n_lanes == 2 ? (unsigned)std::min<uint64_t>(ln.n, 2ull * sms) : (unsigned)ln.n;
-                        if (vec) knn_merge_fast_kernel<true><<<mgrid, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt, ln.n);
-                        else knn_merge_fast_kernel<false><<<mgrid, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt, ln.n);
+                        fast_kernel<<<mgrid, 128, fast_smem, st>>>(l_top, K, l_cand, l_cnt, cap, l_tau, fast_sn, lr, l_work, l_work_cnt, ln.n);
                         // (two lanes: a handful of CTAs — its 34 KB sort buffer does not fit beside a filter CTA, and the list is
                         // normally empty)
                         knn_merge_kernel<<<(unsigned)std::min<uint64_t>(ln.n, n_lanes == 2 ? 16ull : 2ull * sms), 256, merge_smem, st>>>(
@@ -925,6 +1003,15 @@ int knn_base_search(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32
                 }
                 t_profile.chunks += 1;
                 lo = hi;
+                if (resync && !resynced && (lo >= resync->rows || lo >= nb)) {
+                    pt.begin();
+                    knn_rank_kernel<<<(unsigned)((nqb + 255) / 256), 256, 0, s>>>(top, K, resync->rank, nqb, resync->d_bound + qs);
+                    const int hrc = resync->hook(resync->user, qs, nqb, (void *)s);
+                    if (hrc != RG_OK) { set_error("rg_knn: the bound re-sync hook failed"); return hrc; }
+                    knn_min_kernel<<<(unsigned)((nqb + 255) / 256), 256, 0, s>>>(tau, resync->d_bound + qs, nqb);
+                    pt.end(t_profile.merge_ms);
+                    resynced = true;
+                }
                 // next chunk: as many rows as seen so far (expected survivors ~K), three times as many while the rows seen
                 // still fit in L2 (tensor-core path without a seed: the re-rank gather of those ~3K survivors never reaches
                 // DRAM, and the fixed per-launch cost of filter + merge dominates there)
@@ -972,7 +1059,7 @@ int knn_device(const float *d_base, uint64_t nb, const float *d_queries, uint64_
     t_profile = KnnProfile{};
     rg_knn_base *kb = new rg_knn_base();
     int rc = knn_base_prepare(kb, d_base, nb, dim, metric, /*from_ws=*/true, s);
-    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s, nullptr, 0);
+    if (rc == RG_OK) rc = knn_base_search(kb, d_queries, nq, K, id_offset, d_ids, d_dists, s, nullptr, 0, nullptr);
     knn_base_free(kb);
     return rc;
 }

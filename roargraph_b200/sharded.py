@@ -283,7 +283,9 @@ class ShardedKnn:
 
     `local_knn(base, q, K, metric, ids, dists, id_offset)` replaces the CUDA entry in the CPU tests."""
 
-    def __init__(self, d_base_shard, metric, row_lo: int, group=None, local_knn=None, share_tau: bool = True):
+    def __init__(self, d_base_shard, metric, row_lo: int, group=None, local_knn=None, share_tau: bool = True,
+                 resync: bool | None = None):
+        import os
         self.group = group
         self.share_tau = share_tau
         self.world, self.rank = _world(group)
@@ -295,6 +297,17 @@ class ShardedKnn:
         if local_knn is None:
             self._kb = rg.KnnBase(d_base_shard, metric)
         self._comm_stream = None
+        # second agreement on the bound inside the shard (rg_knn_base_search_resync_dev): after a fifth of the SMALLEST
+        # shard's rows — the same point on every rank, so the collectives pair up
+        if resync is None:
+            resync = os.environ.get("RG_KNN_RESYNC", "0") == "1"   # opt-in: ~2 % on one rank's share, not measured to pay at N = 8
+        self.resync_rows = None
+        if resync and share_tau and self.world > 1 and local_knn is None:
+            import torch
+            import torch.distributed as dist
+            n = torch.tensor([d_base_shard.shape[0]], dtype=torch.int64, device=d_base_shard.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MIN, group=group)
+            self.resync_rows = int(os.environ.get("RG_KNN_RESYNC_ROWS", int(n.item()) // 5))
 
     def close(self):
         if self._kb is not None:
@@ -329,6 +342,7 @@ class ShardedKnn:
         bufs = [None, None]
         events = [None, None]
         taus = [torch.empty(min(nq, batch), dtype=torch.float32, device=dev) for _ in range(2)] if shared else None
+        bounds = [torch.empty(min(nq, batch), dtype=torch.float32, device=dev) for _ in range(2)] if shared else None
         starts = list(range(0, nq, batch))
         bound = self._start_bound(d_queries[0:min(nq, batch)], K, taus[0]) if shared and starts else None
         for bi, lo in enumerate(starts):
@@ -351,8 +365,15 @@ class ShardedKnn:
                 if bi + 1 < len(starts):
                     nlo = starts[bi + 1]
                     bound = self._start_bound(d_queries[nlo:min(nq, nlo + batch)], K, taus[slot ^ 1])
-                self._kb.search_seeded_dev(q, K, tau[:n], loc_i[:n], loc_d[:n], id_offset=0, stream=torch.cuda.current_stream(),
-                                           bound_rows=G * 65536)
+                if self.resync_rows is not None:
+                    b = bounds[slot]
+                    self._kb.search_resync_dev(
+                        q, K, tau[:n], loc_i[:n], loc_d[:n], -(-K // G), self.resync_rows, b,
+                        lambda off, cnt: dist.all_reduce(b[off:off + cnt], op=dist.ReduceOp.MAX, group=self.group),
+                        id_offset=0, stream=torch.cuda.current_stream(), bound_rows=G * 65536)
+                else:
+                    self._kb.search_seeded_dev(q, K, tau[:n], loc_i[:n], loc_d[:n], id_offset=0,
+                                               stream=torch.cuda.current_stream(), bound_rows=G * 65536)
             elif self._local is not None:
                 self._local(self._base, q, K, self.metric, loc_i[:n], loc_d[:n], self.row_lo)
             else:

@@ -32,6 +32,17 @@ for name, bound_rows in (("growing", 0), ("whole_if_fits", G * 65536)):
         best = dt if best is None else min(best, dt)
     out[name] = {"ms": best * 1e3, "frac": 2.0 * nq * rows * dim / best / 1e12 / peaks["bf16_tflops_sustained"],
                  "short_lists": int((ids < 0).sum().item())}
+# one re-sync inside the shard; the other shards' part of the maximum is emulated by this shard's own value
+bound = torch.empty(nq, dtype=torch.float32, device=dev)
+for frac in (0.1, 0.2):
+    best = None
+    for rep in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        kb.seed_dev(train, K, -(-K // G), tau)
+        kb.search_resync_dev(train, K, tau, ids, d, -(-K // G), int(rows * frac), bound, lambda off, cnt: None, bound_rows=0)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out[f"resync_at_{frac}"] = {"ms": best * 1e3, "frac": 2.0 * nq * rows * dim / best / 1e12 / peaks["bf16_tflops_sustained"]}
 best = None
 for rep in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -33,8 +33,8 @@ def main():
     want_d = torch.empty((nq, K), dtype=torch.float32, device=dev)
     rg.knn_dev(base, q, K, metric, want_i, want_d)
     ok = True
-    for share in (True, False):
-        sk = ShardedKnn(shard, metric, lo, share_tau=share)
+    for share, resync in ((True, True), (True, False), (False, False)):
+        sk = ShardedKnn(shard, metric, lo, share_tau=share, resync=resync)
         got_i, got_d = sk.search(q, K, batch=batch)
         torch.cuda.synchronize()
         same = bool((got_i == want_i).all().item()) and bool((got_d == want_d).all().item())
@@ -53,7 +53,7 @@ def main():
         flags = torch.tensor([int(same), int(same_slice), int(untouched)], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(f"share_tau={share} full={int(flags[0])} slice={int(flags[1])} untouched={int(flags[2])}", flush=True)
+            print(f"share_tau={share} resync={resync} full={int(flags[0])} slice={int(flags[1])} untouched={int(flags[2])}", flush=True)
         ok = ok and bool(flags.min().item())
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -71,3 +71,27 @@ def test_group_knn_equals_oracle(oracle, G, monkeypatch):
         monkeypatch.delenv("RG_KNN_HOST_BATCH")
         assert (ids2 == ids).all() and (dists2.view(np.uint32) == dists.view(np.uint32)).all()
     grp.close()
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_group_knn_shared_bound_at_scale_equals_single_gpu(G, monkeypatch):
+    """Shards large enough for the tensor-core seed pass (the shared bound really cuts the per-shard lists), with and without
+    the re-sync of the bound inside the shard (RG_KNN_RESYNC=1), several host batches: ids and distance bits of the single-GPU
+    kNN over the whole base."""
+    if _n_gpus() < G:
+        pytest.skip(f"needs {G} GPUs")
+    rng = np.random.default_rng(5)
+    nb, nq, dim, K = 520_000, 2500, 200, 100
+    cent = rng.standard_normal((64, dim)).astype(np.float32)
+    base = (cent[rng.integers(0, 64, nb)] + 0.7 * rng.standard_normal((nb, dim))).astype(np.float32)
+    q = (cent[rng.integers(0, 64, nq)] + 0.9 * rng.standard_normal((nq, dim))).astype(np.float32)
+    grp = rg.Group(G)
+    monkeypatch.setenv("RG_KNN_HOST_BATCH", "1024")
+    for metric in ("ip", "l2"):
+        want_i, want_d = rg.knn(base, q, K, metric)
+        for resync in ("0", "1"):
+            monkeypatch.setenv("RG_KNN_RESYNC", resync)
+            ids, dists = grp.knn(base, q, K, metric)
+            assert (ids == want_i).all(), (metric, resync)
+            assert (dists.view(np.uint32) == want_d.view(np.uint32)).all(), (metric, resync)
+    grp.close()

@@ -1,5 +1,7 @@
 """GPU parity tests for the brute-force kNN (exact_knn) through the C-ABI, against the oracle and the reference's
 compute_groundtruth output stored in tests/golden."""
+import os
+
 import numpy as np
 import pytest
 
@@ -201,9 +203,14 @@ def test_knn_shared_tau_across_shards_is_exact(knn_mode):
         for g, kb in enumerate(shards):
             li = torch.empty((nq, K), dtype=torch.int32, device="cuda")
             ld = torch.empty((nq, K), dtype=torch.float32, device="cuda")
-            # bound_rows: with a generous claim the whole shard goes through ONE filter + merge pair (and falls back to the
-            # growing schedule if a list overflows); both schedules must give the same lists
-            kb.search_seeded_dev(d_q, K, tau, li, ld, bound_rows=(0 if g == 0 else 8 * nb))
+            # bound_rows + RG_KNN_WHOLE_SHARD=1: with a generous claim the whole shard goes through ONE filter + merge pair
+            # (and falls back to the growing schedule if a list overflows); both schedules must give the same lists
+            if g == 1:
+                os.environ["RG_KNN_WHOLE_SHARD"] = "1"
+            try:
+                kb.search_seeded_dev(d_q, K, tau, li, ld, bound_rows=(0 if g == 0 else 8 * nb))
+            finally:
+                os.environ.pop("RG_KNN_WHOLE_SHARD", None)
             short += int((li < 0).sum().item())
             rg.topk_pack_dev(ld, li, lo[g], packed[g])
         out_i = torch.empty((nq, K), dtype=torch.int32, device="cuda")
@@ -216,3 +223,91 @@ def test_knn_shared_tau_across_shards_is_exact(knn_mode):
         assert (out_d.cpu().numpy().view(np.uint32) == want_d.view(np.uint32)).all(), metric
         for kb in shards:
             kb.close()
+
+
+def test_knn_bound_resync_inside_the_shard_is_exact(knn_mode):
+    """rg_knn_base_search_resync_dev on one GPU: two shards, the seed bound as above, plus ONE re-sync inside each shard whose
+    hook plays the other shard's part — it raises the published rank-ceil(K/2) distances to the maximum with the OTHER shard's
+    final rank-ceil(K/2) distance (a value that shard certainly holds ceil(K/2) rows under).  The merged lists must equal the
+    unsharded answer bit for bit, the hook must run exactly once per call, and the tightened bound must really cut work."""
+    if knn_mode != "tc":
+        pytest.skip("the seed pass belongs to the 2-CTA tensor-core filter")
+    import torch
+    rng = np.random.default_rng(18)
+    nb, nq, dim, K = 600_000, 2500, 200, 100
+    cent = rng.standard_normal((64, dim)).astype(np.float32)
+    base = (cent[rng.integers(0, 64, nb)] + 0.7 * rng.standard_normal((nb, dim))).astype(np.float32)
+    q = (cent[rng.integers(0, 64, nq)] + 0.9 * rng.standard_normal((nq, dim))).astype(np.float32)
+    d_base, d_q = torch.from_numpy(base).cuda(), torch.from_numpy(q).cuda()
+    G, lo, r = 2, [0, nb // 2 + 1280, nb], 50
+    for metric in ("ip", "l2"):
+        want_i, want_d = rg.knn(base, q, K, metric)
+        shards = [rg.KnnBase(d_base[lo[g]:lo[g + 1]], metric) for g in range(G)]
+        taus, finals = [], []
+        for kb in shards:
+            t = torch.empty(nq, dtype=torch.float32, device="cuda")
+            kb.seed_dev(d_q, K, r, t)
+            taus.append(t)
+            li = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+            ld = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+            kb.search_dev(d_q, K, li, ld)
+            finals.append(ld[:, r - 1].contiguous())
+        tau = torch.maximum(taus[0], taus[1])
+        packed = torch.empty((G, nq, K), dtype=torch.int64, device="cuda")
+        for resync_rows in (0, (nb // 2) // 5, 10 * nb):      # after the first chunk / a fifth of the shard / after the last chunk
+            calls, tight = [], []
+            for g, kb in enumerate(shards):
+                li = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+                ld = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+                bound = torch.full((nq,), -1.0, dtype=torch.float32, device="cuda")
+
+                def reduce_max(off, cnt, bound=bound, g=g):
+                    calls.append((g, off, cnt))
+                    mine = bound[off:off + cnt]
+                    tight.append(float((torch.maximum(mine, finals[1 - g][off:off + cnt]) < tau[off:off + cnt]).float().mean()))
+                    torch.maximum(mine, finals[1 - g][off:off + cnt], out=mine)
+
+                kb.search_resync_dev(d_q, K, tau, li, ld, r, resync_rows, bound, reduce_max)
+                rg.topk_pack_dev(ld, li, lo[g], packed[g])
+            assert calls == [(0, 0, nq), (1, 0, nq)], calls
+            out_i = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+            out_d = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+            rg.topk_merge_packed_dev(packed, out_d, out_i)
+            torch.cuda.synchronize()
+            assert (out_i.cpu().numpy() == want_i).all(), (metric, resync_rows)
+            assert (out_d.cpu().numpy().view(np.uint32) == want_d.view(np.uint32)).all(), (metric, resync_rows)
+            if resync_rows == (nb // 2) // 5:
+                assert min(tight) > 0.5, tight   # the re-synced bound is below the seed bound for most queries
+        # a hook that fails must surface as an error, not as a hang or a wrong answer
+        with pytest.raises(ZeroDivisionError):
+            shards[0].search_resync_dev(d_q, K, tau, li, ld, r, 0, bound, lambda off, cnt: 1 // 0)
+        for kb in shards:
+            kb.close()
+
+
+def test_knn_merge_by_rank_equals_full_sort(knn_mode, monkeypatch):
+    """The re-rank kernel's two list updates — sort the new entries and merge with the sorted list by rank (default), or sort
+    everything (RG_KNN_MERGE_RANK=0) — must leave identical lists: ids and distance bits, short lists (K close to the rows
+    seen in the first chunks) and long ones."""
+    if knn_mode != "tc":
+        pytest.skip("the fast merge kernel belongs to the tensor-core pipeline")
+    import torch
+    rng = np.random.default_rng(21)
+    nb, nq, dim = 300_000, 3000, 200
+    base = rng.standard_normal((nb, dim)).astype(np.float32) * (1.0 + 0.3 * rng.random((nb, 1), dtype=np.float32))
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    base[1000:1040] = base[5]                 # exact duplicates: equal distances, ordered by id
+    d_base, d_q = torch.from_numpy(base).cuda(), torch.from_numpy(q).cuda()
+    for metric in ("ip", "l2"):
+        for K in (1, 10, 100, 500):
+            got = []
+            for flag in ("1", "0"):
+                monkeypatch.setenv("RG_KNN_MERGE_RANK", flag)
+                ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+                dd = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+                rg.knn_dev(d_base, d_q, K, metric, ids, dd)
+                torch.cuda.synchronize()
+                got.append((ids.cpu().numpy(), dd.cpu().numpy().view(np.uint32)))
+            assert (got[0][0] == got[1][0]).all(), (metric, K)
+            assert (got[0][1] == got[1][1]).all(), (metric, K)
+            assert (got[0][0] >= 0).all()

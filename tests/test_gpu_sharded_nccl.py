@@ -27,5 +27,6 @@ def test_sharded_knn_over_nccl_equals_single_gpu(world, metric):
            "--master-port", str(port), os.path.join(HERE, "_nccl_knn_worker.py"), metric]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "share_tau=True full=1 slice=1 untouched=1" in r.stdout
-    assert "share_tau=False full=1 slice=1 untouched=1" in r.stdout
+    assert "share_tau=True resync=True full=1 slice=1 untouched=1" in r.stdout
+    assert "share_tau=True resync=False full=1 slice=1 untouched=1" in r.stdout
+    assert "share_tau=False resync=False full=1 slice=1 untouched=1" in r.stdout
