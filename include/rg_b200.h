@@ -156,8 +156,9 @@ int rg_knn_base_search_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq,
  * below the maximum, G * rank >= K.  rg_knn_base_search_seeded_dev then scores the batch with that bound in force from row 0:
  * a shard re-ranks ~K/4 instead of ~K * log2(rows) survivors per query.  Its per-shard lists may hold fewer than K entries
  * (id -1, distance +inf behind them): every row of the global top-K is at or below the bound, so the MERGED top-K is exact.
- * bound_rows = the number of rows the bound is (about) the K-th best of (G x 65 536; 0 = unknown): when the survivors expected
- * over the whole shard fit a candidate list, the shard is scored in ONE filter + merge launch pair. */
+ * bound_rows = the number of rows the bound is (about) the K-th best of (G x 65 536; 0 = unknown): with RG_KNN_WHOLE_SHARD=1
+ * in the environment and the survivors expected over the whole shard fitting a candidate list, the shard is scored in ONE
+ * filter + merge launch pair (measured slower than the default growing chunks; an option). */
 int rg_knn_base_seed_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, uint32_t rank, float *d_tau, void *stream);
 int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
                                   const float *d_tau, uint64_t bound_rows, int32_t *d_ids, float *d_dists, void *stream);
