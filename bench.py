@@ -17,7 +17,7 @@ at the smallest L_pq of the reference's canonical sweep (README.md:118) whose re
 Sub-records (each carries its own workload, timing and roofline; a failure is recorded under its key, never fatal):
   batch100k / batch10k   the other batch size on the same index
   knn        BASELINE configs[3]: compute_groundtruth's exact_knn, 10 M base x 10 M training queries, K = 100, base sharded
-             over the ranks (tcgen05 bf16 filter + exact fp32 re-rank, packed all-gather + merge per 151 552-query batch);
+             over the ranks (tcgen05 bf16 filter + exact fp32 re-rank, shared bound, packed exchange + merge per 151 552-query batch);
              at N = 1 with the reference's MKL path timed on a slice beside it (cpu_baseline)
   bipartite  SearchBipartiteGraph (A2) on a 1 M x 200 base with 3 M training queries (N = 1)
   laion      BASELINE configs[2]: 10 M x 512 cosine, 10 000 queries (N = 1)
@@ -525,14 +525,14 @@ def leg_knn(cx, w):
                          "kernel": "knn_tc_filter_pair_kernel (tcgen05 bf16 filter) + knn_merge_fast_kernel (fp32 re-rank)",
                          "flops": "2 * nq * nb * d with the true d (the MMA runs K = 208)"},
             "phases_ms_one_batch": {**phases, "batch": nb1, "note": "device time per phase of one 151 552-query batch on this "
-                                    "rank (separate synchronising pass); the exchange (packed all-gather + merge) runs on a "
+                                    "rank (separate synchronising pass); the exchange (packed all-to-all of the slices + merge) runs on a "
                                     "side stream under the next batch's filter"},
             "check": {"sample": ns, "ids_equal_to_fp32_simt_path": same, "max_rel_distance_diff": max_rel,
                       "note": "independent fp32 path with a different accumulation order: distances agree to ~1e-6 relative and "
                               "the ids differ only where two rows are closer than that (near-ties swap places); the reference "
                               "itself is compared in cpu_baseline.ids_equal_to_gpu_fraction and tests/test_gpu_knn.py (MKL, 200 k x 200 k)"},
             "note": "wall clock of the whole job between device synchronisations (max over ranks): base preparation, every "
-                    "batch's conversion, tau seed pass, filter, re-rank/merge, unpack, packed all-gather + merge of the rank's "
+                    "batch's conversion, tau seed pass, filter, re-rank/merge, unpack, packed all-to-all + merge of the rank's "
                     "slice; queries and results resident in HBM"}
 
 
