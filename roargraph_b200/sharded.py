@@ -25,6 +25,12 @@ def shard_range(nb: int, shard: int, n_shards: int):
     return shard * nb // n_shards, (shard + 1) * nb // n_shards
 
 
+# kernels of this package behind one local graph search (rg_search_roargraph_dev / rg_search_bipartite_dev): tags_clear_kernel,
+# tags_reset_kernel (visited-tag maintenance in front of every launch) and beam_search_kernel — what an ncu launch list of
+# a step shows (profiles/r2_launches_10M.csv); pack and merge are one kernel each
+SEARCH_KERNELS = 3
+
+
 def _world(group=None):
     import torch.distributed as dist
 
@@ -149,8 +155,7 @@ class ShardedRoarIndex:
                 self._search_local(d_q, k, L_pq, out_ids, out_dists, d_cmps, d_hops)
                 if self.row_lo:
                     out_ids.add_((out_ids != NO_ID).to(out_ids.dtype) * self.row_lo)  # the sentinel stays what it is
-                    return 2
-                return 1
+                return SEARCH_KERNELS
         loc_i, loc_d, packed, gathered = self._scratch(d_q.shape[0], ks, d_q.device)
         self._search_local(d_q, ks, L_pq, loc_i, loc_d, d_cmps, d_hops)
         pack_topk(loc_d, loc_i, self.row_lo, out=packed)  # local -> global ids, like start_id in compute_groundtruth.cpp:413
@@ -159,7 +164,7 @@ class ShardedRoarIndex:
         else:
             gathered.copy_(packed)
         merge_packed(gathered.view(self.world, d_q.shape[0], ks), out_dists, out_ids)
-        return 3
+        return SEARCH_KERNELS + 2
 
     def _e2e_buffers(self, nq, dim, k, device):
         import torch
@@ -241,7 +246,7 @@ class ReplicatedRoarIndex:
         nq = d_q_all.shape[0]
         if self.world == 1:
             self._search_local(d_q_all, k, L_pq, out_ids, out_dists)
-            return 1
+            return SEARCH_KERNELS
         per = -(-nq // self.world)
         lo = min(self.rank * per, nq)
         hi = min(lo + per, nq)
@@ -256,12 +261,12 @@ class ReplicatedRoarIndex:
         launches = 0
         if hi - lo == per:
             self._search_local(d_q_all[lo:hi], k, L_pq, loc_i, loc_d)  # rows of a row-major batch: contiguous, in place
-            launches = 1
+            launches = SEARCH_KERNELS
         elif hi > lo:
             q_loc[:hi - lo].copy_(d_q_all[lo:hi])
             q_loc[hi - lo:].copy_(d_q_all[hi - 1:hi].expand(per - (hi - lo), -1))
             self._search_local(q_loc, k, L_pq, loc_i, loc_d)
-            launches = 1
+            launches = SEARCH_KERNELS
         pack_topk(loc_d, loc_i, 0, out=packed)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)  # one collective for ids and distances together
         # rank r's block starts at r * per: contiguous in query order, padding only at the end

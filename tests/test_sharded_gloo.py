@@ -219,7 +219,7 @@ def _sharded_search_worker(rank, world, port, out):
     for ks in (10, 6):
         ids = torch.empty((nq, 10), dtype=torch.int32)
         dists = torch.empty((nq, 10), dtype=torch.float32)
-        assert sidx.search_dev(torch.from_numpy(g.queries), 10, 32, ids, dists, k_shard=ks) == 3
+        assert sidx.search_dev(torch.from_numpy(g.queries), 10, 32, ids, dists, k_shard=ks) == 5  # tag maintenance (2) + search + pack + merge
         res[ks] = (ids.numpy().copy(), dists.numpy().copy())
     if rank == 0:
         np.savez(out, i10=res[10][0], d10=res[10][1], i6=res[6][0], d6=res[6][1])
