@@ -163,8 +163,8 @@ int rg_knn_base_seed_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, u
 int rg_knn_base_search_seeded_dev(rg_knn_base *kb, const float *d_queries, uint64_t nq, uint32_t K, int32_t id_offset,
                                   const float *d_tau, uint64_t bound_rows, int32_t *d_ids, float *d_dists, void *stream);
 /* The same with ONE re-sync of the bound inside the shard: at the first chunk boundary at or past `resync_rows` rows (after the
- * last chunk when the shard is shorter, so that every shard calls the hook the same number of times: once per batch of up to
- * 151 552 queries) the shard writes its `rank`-th best EXACT distance so far into d_bound[q] (+inf while its list is shorter)
+ * last chunk when the shard is shorter, so that every shard calls the hook the same number of times: once per internal query
+ * batch — 151 552 queries for K <= 512 on a 148-SM part; the count depends only on nq, K and the SM count) the shard writes its `rank`-th best EXACT distance so far into d_bound[q] (+inf while its list is shorter)
  * and calls hook(user, q_off, n, stream), which must reduce d_bound[q_off, q_off + n) to the MAXIMUM over the shards on
  * `stream` (one all-reduce) and return RG_OK; the search then continues with tau = min(tau, d_bound).  With rank * G >= K the
  * maximum bounds the global K-th best distance exactly like the seed bound, but from re-ranked rows of a fifth of the base
