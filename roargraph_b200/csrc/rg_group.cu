@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "rg_internal.h"
+#include "rg_rendezvous.h"
 
 namespace rg {
 namespace {
@@ -89,7 +90,16 @@ namespace {
 
 // fn(shard) on one host thread per GPU of the group, each with its device current; the first failure's code and message
 // are handed back to the calling thread (rg_last_error is thread-local)
-int run_on_all(rg_group *g, const std::function<int(int)> &fn) {
+// kPeerFailed: this worker is fine but left because another one failed before a collective (Rendezvous); the caller gets the
+// failing worker's code and message.  A worker that fails in the prologue below reports to `rv` (when the call uses one) so
+// that its peers do not wait for it.
+constexpr int kPeerFailed = -100;
+int peer_failed() {
+    set_error("another GPU of the group failed before the exchange");
+    return kPeerFailed;
+}
+
+int run_on_all(rg_group *g, const std::function<int(int)> &fn, Rendezvous *rv = nullptr) {
     std::vector<int> rc(g->n, RG_OK);
     std::vector<std::string> msg(g->n);
     std::vector<std::thread> th;
@@ -102,15 +112,18 @@ int run_on_all(rg_group *g, const std::function<int(int)> &fn) {
             } else {
                 rc[s] = ensure_device_ready();
                 if (rc[s] == RG_OK) rc[s] = fn(s);
+                else if (rv) rv->agree(false);
             }
+            if (e != cudaSuccess && rv) rv->agree(false);
             if (rc[s] != RG_OK) msg[s] = rg_last_error();
         });
     for (auto &t : th) t.join();
-    for (int s = 0; s < g->n; ++s)
-        if (rc[s] != RG_OK) {
-            set_error("GPU " + std::to_string(g->dev[s]) + ": " + msg[s]);
-            return rc[s];
-        }
+    for (int pass = 0; pass < 2; ++pass)  // a worker's own failure first, "a peer failed" only if nothing better is known
+        for (int s = 0; s < g->n; ++s)
+            if (rc[s] != RG_OK && (pass == 1 || rc[s] != kPeerFailed)) {
+                set_error("GPU " + std::to_string(g->dev[s]) + ": " + msg[s]);
+                return rc[s] == kPeerFailed ? RG_ECUDA : rc[s];
+            }
     return RG_OK;
 }
 
@@ -276,15 +289,19 @@ int rg_sharded_search_roargraph(rg_sharded_index *si, const float *queries, uint
     const int G = g->n;
     const uint32_t dim = si->dim;
     const uint64_t per = ((uint64_t)nq + G - 1) / G;  // query rows uploaded per GPU; the rest arrives over NVLink
+    Rendezvous rv(G);
     return run_on_all(g, [&](int s) {
         auto &sc = si->scratch[s];
         cudaStream_t st = g->stream[s];
         int rc;
-        if ((rc = sc.q.reserve((size_t)G * per * dim)) != RG_OK) return rc;
-        if ((rc = sc.ids.reserve((size_t)nq * k)) != RG_OK) return rc;
-        if ((rc = sc.dists.reserve((size_t)nq * k)) != RG_OK) return rc;
-        if ((rc = sc.packed.reserve((size_t)nq * k)) != RG_OK) return rc;
-        if ((rc = sc.gathered.reserve((size_t)G * nq * k)) != RG_OK) return rc;
+        if ((rc = sc.q.reserve((size_t)G * per * dim)) == RG_OK && (rc = sc.ids.reserve((size_t)nq * k)) == RG_OK &&
+            (rc = sc.dists.reserve((size_t)nq * k)) == RG_OK && (rc = sc.packed.reserve((size_t)nq * k)) == RG_OK &&
+            (rc = sc.gathered.reserve((size_t)G * nq * k)) == RG_OK && s == 0 &&
+            (rc = sc.out_i.reserve((size_t)nq * k)) == RG_OK)
+            rc = sc.out_d.reserve((size_t)nq * k);
+        // nobody enters the collectives unless every GPU has its buffers (a worker that ran out of memory alone would leave
+        // its peers blocked in the all-gather)
+        if (!rv.agree(rc == RG_OK)) return rc != RG_OK ? rc : peer_failed();
         const uint64_t lo = std::min<uint64_t>((uint64_t)s * per, nq), hi = std::min<uint64_t>(lo + per, nq);
         float *mine = sc.q.p + (size_t)s * per * dim;
         if (hi > lo) RG_CUDA(cudaMemcpyAsync(mine, queries + lo * dim, (hi - lo) * dim * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -296,15 +313,13 @@ int rg_sharded_search_roargraph(rg_sharded_index *si, const float *queries, uint
         if (G > 1) RG_NCCL(g_nccl.AllGather(sc.packed.p, sc.gathered.p, (size_t)nq * k, ncclUint64, g->comm[s], st));  // the ONE exchange
         else RG_CUDA(cudaMemcpyAsync(sc.gathered.p, sc.packed.p, (size_t)nq * k * 8, cudaMemcpyDeviceToDevice, st));
         if (s == 0) {  // every rank holds every list; the first one merges and answers
-            if ((rc = sc.out_i.reserve((size_t)nq * k)) != RG_OK) return rc;
-            if ((rc = sc.out_d.reserve((size_t)nq * k)) != RG_OK) return rc;
             rc = topk_merge_packed_device(sc.gathered.p, G, nq, k, k, 0, nq, sc.out_d.p, sc.out_i.p, st);
             if (rc != RG_OK) return rc;
             RG_CUDA(cudaMemcpyAsync(ids, sc.out_i.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             RG_CUDA(cudaMemcpyAsync(dists, sc.out_d.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
         return rg_index_check(si->shard[s], st);  // synchronises; "not enough results" on a shard surfaces here
-    });
+    }, &rv);
 }
 
 int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queries, uint64_t nq, uint32_t dim, uint32_t K,
@@ -323,28 +338,34 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
     if (const char *rr = getenv("RG_KNN_RESYNC_ROWS")) resync_rows = strtoull(rr, nullptr, 10);
     const char *re = getenv("RG_KNN_RESYNC");
     const bool resync_on = re && re[0] == '1';
+    if (K > nb / G) { set_error("rg_group_knn: K exceeds a shard's rows"); return RG_EINVAL; }  // the smallest shard
+    Rendezvous rv(G);
     return run_on_all(g, [&](int s) {
         cudaStream_t st = g->stream[s];
         const uint64_t lo = shard_lo(nb, s, G), hi = shard_lo(nb, s + 1, G);
-        if (K > hi - lo) { set_error("rg_group_knn: K exceeds a shard's rows"); return RG_EINVAL; }
         float *d_base = nullptr;
         cudaError_t e = cudaMalloc(&d_base, (hi - lo) * dim * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(d_base, base + lo * dim, (hi - lo) * dim * sizeof(float), cudaMemcpyHostToDevice);
+        int rc = RG_OK;
+        rg_knn_base *kb = nullptr;
         if (e != cudaSuccess) {
             if (d_base) cudaFree(d_base);
-            return cuda_fail(e, "rg_group_knn: base shard upload");
+            rc = cuda_fail(e, "rg_group_knn: base shard upload");
+        } else {
+            rc = knn_base_new(&kb, d_base, d_base, hi - lo, dim, metric);  // the object owns d_base from here
         }
-        rg_knn_base *kb = nullptr;
-        int rc = knn_base_new(&kb, d_base, d_base, hi - lo, dim, metric);  // the object owns d_base from here
-        if (rc != RG_OK) return rc;
         DevBuf<float> q, dd, out_d, tau, bound;
         DevBuf<int32_t> di;
         DevBuf<uint32_t> out_i;
         DevBuf<unsigned long long> packed, gathered;
-        if ((rc = q.reserve((size_t)G * per * dim)) == RG_OK && (rc = dd.reserve(batch * K)) == RG_OK &&
+        if (rc == RG_OK && (rc = q.reserve((size_t)G * per * dim)) == RG_OK && (rc = dd.reserve(batch * K)) == RG_OK &&
             (rc = di.reserve(batch * K)) == RG_OK && (rc = packed.reserve(batch * K)) == RG_OK &&
             (rc = gathered.reserve((size_t)G * batch * K)) == RG_OK && (rc = out_d.reserve(batch * K)) == RG_OK &&
-            (rc = out_i.reserve(batch * K)) == RG_OK && (rc = tau.reserve(batch)) == RG_OK && (rc = bound.reserve(batch)) == RG_OK) {
+            (rc = out_i.reserve(batch * K)) == RG_OK && (rc = tau.reserve(batch)) == RG_OK)
+            rc = bound.reserve(batch);
+        // nobody enters the collectives unless every GPU holds its shard and its buffers
+        if (!rv.agree(rc == RG_OK) && rc == RG_OK) rc = peer_failed();
+        if (rc == RG_OK) {
             for (uint64_t q0 = 0; q0 < nq && rc == RG_OK; q0 += batch) {
                 const uint64_t n = std::min(batch, nq - q0);
                 const uint64_t pr = (n + G - 1) / G;  // rows of this batch uploaded by (and merged on) each GPU
@@ -408,10 +429,10 @@ int rg_group_knn(rg_group *g, const float *base, uint64_t nb, const float *queri
         gathered.release();
         out_d.release();
         out_i.release();
-        knn_base_free(kb);
+        if (kb) knn_base_free(kb);
         knn_release_workspace();
         return rc;
-    });
+    }, &rv);
 }
 
 }  // extern "C"

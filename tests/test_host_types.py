@@ -81,3 +81,15 @@ def test_mirror_headers_are_self_contained(tmp_path):
         src.write_text(f'#include "{h}"\nint main() {{ return 0; }}\n')
         subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", MIRROR_INC,
                                "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_rendezvous_gives_every_worker_the_same_verdict(tmp_path, n):
+    """roargraph_b200/csrc/rg_rendezvous.h (the agreement the rg_group_* workers reach before they enter a collective): every
+    thread sees the AND of all reports, round after round, with the object reused."""
+    exe = str(tmp_path / "rendezvous")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I", os.path.join(ROOT, "roargraph_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "cpp", "rendezvous_driver.cpp"), "-o", exe])
+    for fail_every in (1, 3, 1000):
+        out = subprocess.run([exe, str(n), "3000", str(fail_every)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and out.stdout.startswith("ok 3000 "), out.stdout + out.stderr
