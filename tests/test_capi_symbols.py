@@ -50,3 +50,15 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"oracle|liboracle|libref_roargraph|_ref/", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_integration_snippets_compile_and_link(tmp_path):
+    """tests/cpp/integration_calls.cpp repeats the C-ABI calls INTEGRATION.md shows a reference maintainer (same argument
+    order and types): it must compile as C++ against include/rg_b200.h and link against the shipped library."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "integration_calls.cpp")
+    out = str(tmp_path / "libintegration_calls.so")
+    libdir = os.path.join(ROOT, "roargraph_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), src,
+                           "-o", out, "-L", libdir, "-l:librg_b200.so", "-Wl,--no-undefined", "-Wl,-rpath," + libdir])
+    assert os.path.getsize(out) > 0
