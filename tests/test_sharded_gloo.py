@@ -117,6 +117,18 @@ def test_two_rank_sharded_knn(tmp_path, oracle):
     assert (z["i"] == full_i).mean() > 0.999
 
 
+def test_three_rank_sharded_knn(tmp_path, oracle):
+    """Three ranks: 17-query batches do not divide by the world size, so the all-to-all slices are padded (sentinel words) and
+    the last rank's slice is short; same answer."""
+    out = str(tmp_path / "knn3.npz")
+    mp.spawn(_knn_worker, args=(3, _free_port(), out), nprocs=3, join=True)
+    z = np.load(out)
+    g = GoldenCase("l2_d104")
+    full_i, full_d = oracle.exact_knn(g.base_raw, g.test_raw, 7, "l2")
+    np.testing.assert_allclose(z["d"], full_d, rtol=1e-5, atol=1e-5)
+    assert (z["i"] == full_i).mean() > 0.999
+
+
 def _replica_worker(rank, world, port, out, nq):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
