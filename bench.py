@@ -150,7 +150,7 @@ def _peaks():
 
 def load_peaks():
     pk = _peaks()
-    if pk:
+    if pk and pk.get("hbm_gbs"):
         return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
@@ -158,7 +158,7 @@ def load_peaks():
 def load_tensor_peak(burst=False):
     pk = _peaks()
     key = "bf16_tflops" if burst else "bf16_tflops_sustained"
-    if pk:
+    if pk and pk.get(key):
         return float(pk[key]), f"measured (MEASURED_PEAKS.json {key})"
     return (1650.0 if burst else 1400.0), "fallback (B200_PROFILING.md, " + ("burst)" if burst else "sustained)")
 
